@@ -1,0 +1,201 @@
+/*
+ * mmdk.h -- C ABI of libmmdk.so: the B200 (sm_100a) guided-diffusion trajectory sampler.
+ *
+ * The reference (yoraish/mmd) has NO FFI/plugin ABI: its hot path is a Python object protocol
+ * (SURVEY.md 8b).  This header is the boundary a maintainer would bind (ctypes stub in INTEGRATION.md)
+ * behind the reference's own classes.  Every entry point names the reference code it replaces; paths are
+ * relative to the reference root, TR = deps/torch_robotics/torch_robotics, MPB =
+ * deps/motion_planning_baselines/mp_baselines.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a DEVICE pointer owned by the caller
+ *     (e.g. torch tensors via data_ptr()); nothing is allocated inside the per-step calls.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); no call synchronises the host.
+ *   - return value: 0 = MMDK_OK, otherwise an MMDK_E* code; mmdk_last_error() gives the message
+ *     (the Python host maps codes to exceptions: ValueError for MMDK_EINVAL, RuntimeError otherwise).
+ *   - trajectories are fp32 [B, H, D] row-major, D = 4 (x, y, vx, vy), H = horizon (64), normalised to [-1, 1]
+ *     by a LimitsNormalizer (mmd/datasets/normalization.py:150-168).  B = n_groups * K: a "group" is one
+ *     (robot, tile) planner call of K samples sharing hard conditions, constraints and the normaliser's
+ *     global clip decision.
+ */
+#ifndef MMDK_H_
+#define MMDK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMDK_OK 0
+#define MMDK_EINVAL 1   /* bad argument / unsupported shape */
+#define MMDK_ECUDA 2    /* CUDA runtime error */
+#define MMDK_ENOMEM 3
+
+#define MMDK_MAX_LEVELS 4
+#define MMDK_MAX_HARD_ROWS 4
+#define MMDK_STATE_DIM 4
+
+/* Thread-local message of the last failing call. */
+const char* mmdk_last_error(void);
+/* Library / device probe: fills sm count, returns MMDK_ECUDA when no sm_100 device is visible. */
+int mmdk_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * TemporalUnet  (mmd/models/diffusion_models/temporal_unet.py:23-174, mmd/models/layers/layers.py:197-398)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mmdk_unet mmdk_unet;
+
+typedef struct {
+  int state_dim;       /* 4 */
+  int horizon;         /* n_support_points, 64 */
+  int unet_input_dim;  /* 32 */
+  int n_levels;        /* len(dim_mults) */
+  int dim_mults[MMDK_MAX_LEVELS];
+  int time_emb_dim;    /* 32 */
+  int n_diffusion_steps; /* T: the time-embedding table is precomputed for t in [0, T) */
+  int self_attention;  /* LinearAttention blocks present (layers.py:210-229) */
+} mmdk_unet_config;
+
+/* Builds the device-resident network from the reference state_dict: `names[i]` is the reference key
+ * (e.g. "downs.0.0.blocks.0.block.0.weight"), `tensors_dev[i]` a contiguous fp32 device tensor in the
+ * reference layout, `numels[i]` its element count.  Replaces TemporalUnet.__init__ + load_state_dict
+ * (mpd.py:154-171).  Weights are re-packed on the device; the time/cond embedding table (TimeEncoder +
+ * every ResidualTemporalBlock.cond_mlp, layers.py:232-258,337-341) is evaluated once for all t. */
+int mmdk_unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names,
+                     const float* const* tensors_dev, const int64_t* numels, void* stream, mmdk_unet** out);
+void mmdk_unet_destroy(mmdk_unet* net);
+
+/* Numerical mode of the conv contractions. */
+#define MMDK_UNET_FP32 0     /* CUDA-core FFMA, fp32 throughout (exact-parity mode) */
+#define MMDK_UNET_TF32 1     /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+#define MMDK_UNET_TF32X3 2   /* tcgen05 3xTF32 error-compensated split */
+
+/* eps = TemporalUnet.forward(x, t, context=None) for an integer timestep t shared by the batch
+ * (temporal_unet.py:121-174; make_timesteps, diffusion_model_base.py:27-29).  x_dev, eps_dev: [B, H, D]. */
+int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B, int t, float* eps_dev, void* stream);
+
+/* Debug/parity tap: copies the precomputed cond table row of timestep t ([n_cond] floats) to out_dev. */
+int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Guide + DDPM step  (mmd/models/diffusion_models/guides.py:152-253, sample_functions.py:41-107,
+ * diffusion_model_base.py:126-160, MPB/planners/costs/cost_functions.py, TR/environments/grid_map_sdf.py)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  /* LimitsNormalizer: mins and (maxs - mins), computed in fp32 by the caller (normalization.py:157-168) */
+  float norm_min[MMDK_STATE_DIM];
+  float norm_range[MMDK_STATE_DIM];
+  /* GridMapSDF (grid_map_sdf.py:84-114): packed (sdf, dsdf/dx, dsdf/dy, 0) per node, [nx, ny] row-major; NULL = no
+   * object field */
+  const float* grid_dev;
+  int nx, ny;
+  float grid_lo[2];       /* limits[0] */
+  float grid_map_dim[2];  /* |limits[1] - limits[0]| */
+  /* hinge margin = link margin (1.1 r) + cutoff margin (robot_planar_disk.py:68, tasks.py:53-58) */
+  float margin;
+  /* workspace boundaries, already scaled by 1.08 (tasks.py:82-84) */
+  float ws_min[2], ws_max[2];
+  /* gradient weights after clipping (mmd_params.py:40-43) and clip norm (guides.py:154) */
+  float w_collision, w_border, w_smooth;
+  float max_grad_norm;
+  /* GP prior (MPB/planners/costs/factors/gp_factor.py:34-50): dt (Phi) and the three distinct entries of Q^-1,
+   * (12 dt^-3, -6 dt^-2, 4 dt^-1) / sigma_gp^2, evaluated by the caller in double and rounded to fp32 as torch does */
+  float dt, gp_q11, gp_q12, gp_q22;
+  /* 1 / sigma_coll^2 (field_factor.py:22) */
+  float coll_inv_sigma2;
+} mmdk_guide_env;
+
+/* Per-group (robot/tile) inputs.  Extra costs = CostConstraint objects (cost_functions.py:275-326), each
+ * differentiated, clipped and weighted separately (mpd.py:331-342,409-412).  Vertex constraints are bucketed by
+ * waypoint: object o of group g covers entries [bucket_ptr[o*(H+1)+h], bucket_ptr[o*(H+1)+h+1]) of `cons_dev`
+ * for waypoint h; an entry is (qx, qy, radius, 0). */
+typedef struct {
+  int n_groups;
+  int K;                        /* samples per group */
+  const float* hard_vals_dev;   /* [n_groups, MMDK_MAX_HARD_ROWS, D] normalised states */
+  const int* hard_rows_dev;     /* [n_groups, MMDK_MAX_HARD_ROWS] waypoint index or -1 (sample_functions.py:8-14) */
+  const int* obj_ptr_dev;       /* [n_groups + 1] range of cost objects per group, or NULL = no extra costs */
+  const float* obj_weight_dev;  /* [n_obj] */
+  const int* bucket_ptr_dev;    /* [n_obj, H + 1] */
+  const float* cons_dev;        /* [n_entries, 4] */
+  /* lock-step peer exchange: unnormalised positions [n_peers, H, 2] of every robot's representative
+   * sample; group g skips row peer_self_dev[g].  One implicit soft CostConstraint per group with ranges (h, h+1).
+   * NULL = off. */
+  const float* peers_dev;
+  const int* peer_self_dev;     /* [n_groups] */
+  int n_peers;
+  float peer_radius, peer_weight;
+} mmdk_groups;
+
+/* One evaluation of GuideManagerTrajectoriesWithVelocity.forward (guides.py:180-226): grad_dev [B,H,D] =
+ * -(sum_k w_k clip(dcost_k/dx_unnormalised)).  Optional taps for parity tests: per-cost raw gradients
+ * raw_dev [n_costs_max, B, H, D] (order: objects, border, GP, extra objects..., peers), NULL to skip. */
+int mmdk_guide_grad(const mmdk_guide_env* env, const mmdk_groups* groups, int H, const float* x_dev,
+                    float* grad_dev, float* raw_dev, int n_costs_max, void* stream);
+
+/* Scalars of one reverse step, gathered on the host from the schedule buffers (`extract`, sample_functions.py:34-37). */
+typedef struct {
+  int do_posterior;      /* 1: x <- q_posterior mean of (x, eps) (diffusion_model_base.py:126-160) */
+  float sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod;
+  float posterior_mean_coef1, posterior_mean_coef2;
+  int clip_denoised;     /* clamp x0 to [-1, 1] (:155) */
+  int predict_epsilon;
+  int n_guide_steps;     /* 0 = unguided (t >= t_start_guide) */
+  int add_noise;         /* 0 when t == 0 (noise[t == 0] = 0, sample_functions.py:76) or noise_dev is NULL */
+  float model_std;       /* exp(0.5 * posterior_log_variance_clipped[t]) */
+  float noise_std;       /* noise_std_extra_schedule_fn(t), 0.5 in MPD (mpd.py:303) */
+  int final_hard_conds;  /* 1: finish with apply_hard_conditioning as p_sample_loop does (diffusion_model_base.py:202) */
+} mmdk_step_scalars;
+
+/* ddpm_sample_fn minus the UNet (sample_functions.py:41-86) + the trailing apply_hard_conditioning of
+ * p_sample_loop (diffusion_model_base.py:202): posterior mean -> n_guide_steps x (x += guide(x); hard conds)
+ * -> x += noise_scale * noise -> hard conds.  x_dev is updated in place; if chain_dev != NULL the new x is also
+ * written there (chain slot of this step).  eps_dev/noise_dev may be NULL when unused. */
+int mmdk_ddpm_step(const mmdk_guide_env* env, const mmdk_groups* groups, const mmdk_step_scalars* sc, int H,
+                   float* x_dev, const float* eps_dev, const float* noise_dev, float* chain_dev, void* stream);
+
+/* Publishes the representative sample of every group for the lock-step exchange: peers_out_dev[g] [H,2] =
+ * unnormalise(x[g*K + rep_index])[:, :2] with the normaliser's clip rule applied to that group. */
+int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, int rep_index, const float* x_dev,
+                       float* peers_out_dev, void* stream);
+
+/* apply_cross_conditioning (sample_functions.py:17-31) for one (m1, ind1) <- (m2, ind2) stitch of an ensemble:
+ * x1[:, ind1, :] = min(x2[:, ind2, :] + rel, bnd); x2[:, ind2, :] = max(x1[:, ind1, :] - rel, -bnd). */
+int mmdk_cross_condition(float* x1_dev, float* x2_dev, int B, int H, int ind1, int ind2, const float rel[MMDK_STATE_DIM],
+                         const float bnd[MMDK_STATE_DIM], void* stream);
+
+/* q_sample (diffusion_model_base.py:425-433): out = a * x_start + b * noise. */
+int mmdk_q_sample(const float* x_start_dev, const float* noise_dev, float a, float b, int64_t n, float* out_dev,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Integer outputs (bit-exact targets)
+ * ------------------------------------------------------------------------------------------------ */
+/* GridMapSDF cell indices (grid_map_sdf.py:93-97): idx_dev [n, 2] int32 for points_dev [n, 2]. */
+int mmdk_cell_index(const mmdk_guide_env* env, const float* points_dev, int64_t n, int32_t* idx_dev, void* stream);
+
+/* RobotPlanarDisk.check_rr_collisions (TR/robots/robot_planar_disk.py:173-203): pos_dev [n_batch, R, 2] ->
+ * coll_dev [n_batch, R, R] uint8 (1 = ||pi - pj|| < margin, diagonal 0); mid_dev [n_batch, R, R, 2] midpoints
+ * (NaN where no collision) or NULL. */
+int mmdk_check_rr_collisions(const float* pos_dev, int64_t n_batch, int R, float margin, uint8_t* coll_dev,
+                             float* mid_dev, void* stream);
+
+/* PlanningTask.get_trajs_collision_and_free + cost_smoothness/path_length (TR/tasks/tasks.py:236-311,
+ * TR/trajectory/metrics.py:7-39, mpd.py:356-382) on UNNORMALISED trajectories trajs_dev [B, H, D]:
+ * free_dev [B] uint8 (no interpolated waypoint in collision AND inside joint limits), cost_dev [B] =
+ * path_length + smoothness, waypoint_coll_dev [B, (H-1)*n_interp] uint8 or NULL. */
+int mmdk_classify_trajs(const mmdk_guide_env* env, const float* trajs_dev, int B, int H, int n_interp, float radius,
+                        const float q_min[2], const float q_max[2], uint8_t* free_dev, float* cost_dev,
+                        uint8_t* waypoint_coll_dev, void* stream);
+
+/* Elementwise unnormalise of a whole chain with the per-call global clip rule disabled/enabled by `clip`
+ * (mpd.py:354: dataset.unnormalize_trajectories on the [T+2, B, H, D] chain). */
+int mmdk_unnormalize(const mmdk_guide_env* env, const float* x_dev, int64_t n_rows, int clip, float* out_dev,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDK_H_ */

@@ -1,0 +1,88 @@
+// C ABI glue of libmmdk: error reporting, device probe, mmdk_unet_* entry points (see include/mmdk.h).
+#include <string>
+
+#include "common.cuh"
+#include "unet.cuh"
+
+namespace mmdk {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return MMDK_OK;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return MMDK_ECUDA;
+}
+
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace mmdk
+
+using namespace mmdk;
+
+struct mmdk_unet {
+  UnetImpl* impl;
+};
+
+extern "C" {
+
+const char* mmdk_last_error(void) { return g_last_error.c_str(); }
+
+int mmdk_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= device) return fail(MMDK_ECUDA, "no CUDA device visible");
+  cudaDeviceProp p{};
+  MMDK_CUDA(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (p.major != 10) return fail(MMDK_ECUDA, "libmmdk is built for sm_100a only; found compute capability " +
+                                                 std::to_string(p.major) + "." + std::to_string(p.minor));
+  return MMDK_OK;
+}
+
+int mmdk_unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names,
+                     const float* const* tensors_dev, const int64_t* numels, void* stream, mmdk_unet** out) {
+  if (!out) return fail(MMDK_EINVAL, "null out");
+  UnetImpl* impl = nullptr;
+  int rc = unet_create(cfg, n_tensors, names, tensors_dev, numels, (cudaStream_t)stream, &impl);
+  if (rc != MMDK_OK) return rc;
+  *out = new mmdk_unet{impl};
+  return MMDK_OK;
+}
+
+void mmdk_unet_destroy(mmdk_unet* net) {
+  if (!net) return;
+  unet_destroy(net->impl);
+  delete net;
+}
+
+int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B, int t, float* eps_dev, void* stream) {
+  if (!net || !x_dev || !eps_dev) return fail(MMDK_EINVAL, "null argument");
+  if (B <= 0) return MMDK_OK;
+  if (t < 0 || t >= net->impl->cfg.n_diffusion_steps) return fail(MMDK_EINVAL, "timestep out of range");
+  if (mode == MMDK_UNET_FP32) return unet_forward_ffma(net->impl, x_dev, B, t, eps_dev, (cudaStream_t)stream);
+  if (mode == MMDK_UNET_TF32 || mode == MMDK_UNET_TF32X3)
+    return unet_forward_tc(net->impl, mode, x_dev, B, t, eps_dev, (cudaStream_t)stream);
+  return fail(MMDK_EINVAL, "unknown UNet mode");
+}
+
+int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond, void* stream) {
+  if (!net) return fail(MMDK_EINVAL, "null argument");
+  if (n_cond) *n_cond = net->impl->n_cond;
+  if (!out_dev) return MMDK_OK;
+  if (t < 0 || t >= net->impl->cfg.n_diffusion_steps) return fail(MMDK_EINVAL, "timestep out of range");
+  int n = net->impl->n_cond;
+  copy_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(net->impl->cond_table + (size_t)t * n, out_dev, n);
+  return check_cuda(cudaGetLastError(), "copy_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace mmdk {
+
+struct TcState;  // tcgen05 executor state (unet_tc.cu)
+
+struct UnetImpl {
+  mmdk_unet_config cfg{};
+  std::vector<Op> ops;       // host copy of the layer program
+  Op* ops_dev = nullptr;
+  float* blob = nullptr;     // packed fp32 weights: conv [cin][k][cout], vectors as-is
+  size_t blob_floats = 0;
+  float* cond_table = nullptr;  // [T][n_cond]
+  int n_cond = 0;
+  int per_sample_floats = 0;    // activation floats per sample for the fp32 executor
+  int ffma_S = 1;               // samples per CTA of the fp32 executor
+  TcState* tc = nullptr;
+};
+
+int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names, const float* const* tensors,
+                const int64_t* numels, cudaStream_t stream, UnetImpl** out);
+void unet_destroy(UnetImpl* net);
+int unet_forward_ffma(const UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream);
+
+// tcgen05 executor (unet_tc.cu)
+int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream);
+void unet_tc_release(UnetImpl* net);
+
+}  // namespace mmdk

@@ -1,0 +1,222 @@
+"""TemporalUnet with the reference's constructor signature and state_dict key layout, executed by libmmdk.
+
+Mirrors mmd/models/diffusion_models/temporal_unet.py:23-174 and mmd/models/layers/layers.py:177-398 as a PARAMETER
+CONTAINER only: the nn.Module tree exists so that `load_state_dict` accepts the reference's checkpoints
+(`downs.0.0.blocks.0.block.0.weight`, ...); `forward` never runs a torch op on the activations -- it hands the
+weights to mmdk_unet_create once and calls mmdk_unet_forward (hand-written sm_100a kernels).
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+UNET_DIM_MULTS = {0: (1, 2, 4), 1: (1, 2, 4, 8)}  # temporal_unet.py:17-20
+
+
+def group_norm_n_groups(n_channels, target_n_groups=8):  # layers.py:392-398
+    if n_channels < target_n_groups:
+        return 1
+    for n_groups in range(target_n_groups, target_n_groups + 10):
+        if n_channels % n_groups == 0:
+            return n_groups
+    return 1
+
+
+class _Conv1dBlock(nn.Module):  # layers.py:279-296 -> keys block.0.* (Conv1d) and block.2.* (GroupNorm)
+    def __init__(self, ci, co, k=5):
+        super().__init__()
+        self.block = nn.Sequential(nn.Conv1d(ci, co, k, padding=k // 2), nn.Identity(),
+                                   nn.GroupNorm(group_norm_n_groups(co), co), nn.Identity(), nn.Identity())
+
+
+class _ResidualTemporalBlock(nn.Module):  # layers.py:326-358
+    def __init__(self, ci, co, cond_dim):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Conv1dBlock(ci, co), _Conv1dBlock(co, co)])
+        self.cond_mlp = nn.Sequential(nn.Identity(), nn.Linear(cond_dim, co), nn.Identity())
+        self.residual_conv = nn.Conv1d(ci, co, 1) if ci != co else nn.Identity()
+
+
+class _Resample(nn.Module):  # layers.py:261-276 -> key conv.*
+    def __init__(self, dim, up):
+        super().__init__()
+        self.conv = nn.ConvTranspose1d(dim, dim, 4, 2, 1) if up else nn.Conv1d(dim, dim, 3, 2, 1)
+
+
+class _LayerNorm(nn.Module):  # layers.py:197-207
+    def __init__(self, dim):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(1, dim, 1))
+        self.b = nn.Parameter(torch.zeros(1, dim, 1))
+
+
+class _LinearAttention(nn.Module):  # layers.py:210-229
+    def __init__(self, dim, heads=4, dim_head=32):
+        super().__init__()
+        self.to_qkv = nn.Conv1d(dim, heads * dim_head * 3, 1, bias=False)
+        self.to_out = nn.Conv1d(heads * dim_head, dim, 1)
+
+
+class _PreNorm(nn.Module):  # layers.py:186-194
+    def __init__(self, dim):
+        super().__init__()
+        self.fn = _LinearAttention(dim)
+        self.norm = _LayerNorm(dim)
+
+
+class _Residual(nn.Module):  # layers.py:177-183
+    def __init__(self, dim):
+        super().__init__()
+        self.fn = _PreNorm(dim)
+
+
+class _TimeEncoder(nn.Module):  # layers.py:232-243
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.encoder = nn.Sequential(nn.Identity(), nn.Linear(dim, dim * 4), nn.Identity(), nn.Linear(dim * 4, dim_out))
+
+
+def sinusoidal_table(n_steps, dim=32):
+    """SinusoidalPosEmb (layers.py:246-258) for t = 0..n_steps-1, evaluated with the reference's own expression so
+    the device never re-derives sin/cos (copy tables from torch to avoid libm drift)."""
+    x = torch.arange(n_steps)
+    half = dim // 2
+    emb = math.log(10000) / (half - 1)
+    emb = torch.exp(torch.arange(half) * -emb)
+    emb = x[:, None] * emb[None, :]
+    return torch.cat((emb.sin(), emb.cos()), dim=-1).to(torch.float32).contiguous()
+
+
+class TemporalUnet(nn.Module):
+    def __init__(self, n_support_points=None, state_dim=None, unet_input_dim=32, dim_mults=(1, 2, 4, 8),
+                 time_emb_dim=32, self_attention=False, conditioning_embed_dim=4, conditioning_type=None,
+                 attention_num_heads=2, attention_dim_head=32, unet_precision="fp32", **kwargs):
+        super().__init__()
+        if conditioning_type not in (None, "None"):
+            # temporal_unet.py:44-58: 'concatenate'/'attention'/'default' need context models no planner builds
+            raise NotImplementedError("only conditioning_type=None is on the sampling path (mpd.py:154-159,210)")
+        self.state_dim = state_dim
+        self.n_support_points = n_support_points
+        self.unet_input_dim = unet_input_dim
+        self.dim_mults = tuple(dim_mults)
+        self.time_emb_dim = time_emb_dim
+        self.self_attention = bool(self_attention)
+        self.conditioning_type = None
+        self.unet_precision = unet_precision
+
+        dims = [state_dim, *[unet_input_dim * m for m in dim_mults]]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        self.time_mlp = _TimeEncoder(32, time_emb_dim)
+        cond_dim = time_emb_dim
+        self.downs = nn.ModuleList([])
+        self.ups = nn.ModuleList([])
+        n_res = len(in_out)
+        for ind, (di, do) in enumerate(in_out):
+            is_last = ind >= (n_res - 1)
+            self.downs.append(nn.ModuleList([
+                _ResidualTemporalBlock(di, do, cond_dim), _ResidualTemporalBlock(do, do, cond_dim),
+                _Residual(do) if self_attention else nn.Identity(), None,
+                _Resample(do, up=False) if not is_last else nn.Identity()]))
+        mid = dims[-1]
+        self.mid_block1 = _ResidualTemporalBlock(mid, mid, cond_dim)
+        self.mid_attn = _Residual(mid) if self_attention else nn.Identity()
+        self.mid_attention = nn.Identity()
+        self.mid_block2 = _ResidualTemporalBlock(mid, mid, cond_dim)
+        for ind, (di, do) in enumerate(reversed(in_out[1:])):
+            self.ups.append(nn.ModuleList([
+                _ResidualTemporalBlock(do * 2, di, cond_dim), _ResidualTemporalBlock(di, di, cond_dim),
+                _Residual(di) if self_attention else nn.Identity(), None, _Resample(di, up=True)]))
+        self.final_conv = nn.Sequential(_Conv1dBlock(unet_input_dim, unet_input_dim), nn.Conv1d(unet_input_dim, state_dim, 1))
+
+        self._handle = None
+        self._handle_key = None
+        self._keepalive = None
+        self._time_table_steps = 1024
+
+    # -- native handle ------------------------------------------------------------------------------------------
+    def _invalidate(self):
+        self._release()
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().mmdk_unet_destroy(self._handle)
+        self._handle = None
+        self._handle_key = None
+        self._keepalive = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return out
+
+    def ensure_time_table(self, n_steps):
+        if n_steps > self._time_table_steps:
+            self._time_table_steps = int(n_steps)
+            self._invalidate()
+
+    def native(self):
+        """mmdk_unet handle for the current weights/device (built lazily, rebuilt after load_state_dict / .to())."""
+        lib = _lib.lib()
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.MMDKError("TemporalUnet parameters must live on a CUDA device (no CPU path)")
+        key = (dev, self._time_table_steps)
+        if self._handle is not None and self._handle_key == key:
+            return self._handle
+        self._release()
+        sd = {k: v.detach().to(torch.float32).contiguous() for k, v in self.state_dict().items()}
+        sd["__sincos_table__"] = sinusoidal_table(self._time_table_steps).to(dev)
+        names = list(sd.keys())
+        cfg = _lib.UnetConfig()
+        cfg.state_dim, cfg.horizon, cfg.unet_input_dim = self.state_dim, self.n_support_points, self.unet_input_dim
+        cfg.n_levels = len(self.dim_mults)
+        for i, m in enumerate(self.dim_mults):
+            cfg.dim_mults[i] = m
+        cfg.time_emb_dim = self.time_emb_dim
+        cfg.n_diffusion_steps = self._time_table_steps
+        cfg.self_attention = int(self.self_attention)
+        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        c_ptrs = (C.c_void_p * len(names))(*[sd[n].data_ptr() for n in names])
+        c_numel = (C.c_int64 * len(names))(*[sd[n].numel() for n in names])
+        out = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.mmdk_unet_create(C.byref(cfg), len(names), c_names, c_ptrs, c_numel, _lib.stream_ptr(), C.byref(out)))
+        self._handle, self._handle_key, self._keepalive = out, key, sd
+        return out
+
+    # -- forward ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, time, context=None, precision=None):
+        """x: [B, H, D] cuda fp32; time: [B] long with one shared value (make_timesteps, diffusion_model_base.py:27)."""
+        if context is not None:
+            raise NotImplementedError("context conditioning is not on the sampling path (mpd.py:210 context=None)")
+        t = int(time[0]) if torch.is_tensor(time) else int(time)
+        return self.forward_t(x, t, precision)
+
+    @torch.no_grad()
+    def forward_t(self, x, t, precision=None, out=None):
+        lib = _lib.lib()
+        x = x.contiguous()
+        assert x.dtype == torch.float32 and x.dim() == 3
+        assert x.shape[1] == self.n_support_points and x.shape[2] == self.state_dim
+        self.ensure_time_table(t + 1)
+        h = self.native()
+        if out is None:
+            out = torch.empty_like(x)
+        mode = _lib.UNET_MODES[precision or self.unet_precision]
+        _lib.check(lib.mmdk_unet_forward(h, mode, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
+        return out

@@ -339,7 +339,8 @@ def build_sdf_grid(env_name, cell_size=0.005, limits=((-1.0, -1.0), (1.0, 1.0)))
     for i in range(pts.shape[0]):  # row by row, as the reference does
         row = pts[i].clone().requires_grad_(True)
         s = env_signed_distance(env_name, row)
-        (g,) = torch.autograd.grad(s.sum(), row, allow_unused=True)
+        # torch.autograd.functional.jacobian returns zeros when the output does not depend on the input (empty envs)
+        g = torch.autograd.grad(s.sum(), row, allow_unused=True)[0] if s.requires_grad else None
         sdf_rows.append(s.detach())
         grad_rows.append(torch.zeros_like(row) if g is None else g)
     return torch.stack(sdf_rows), torch.stack(grad_rows)
@@ -403,7 +404,8 @@ class GuideSpec:
                  w_collision=2e-2, w_smooth=8e-2, max_grad_norm=1.0, sigma_coll=1.0, sigma_gp=1.0):
         self.grid = grid
         self.normalizer = normalizer
-        self.margin = ROBOT_RADIUS * 1.1 + cutoff_margin  # robot_planar_disk.py:68 + tasks.py obstacle_cutoff_margin
+        # distance_fields.py:115: fp32 link-margin tensor (robot_planar_disk.py:68) + python cutoff margin
+        self.margin = torch.tensor([ROBOT_RADIUS * 1.1], dtype=torch.float32) + cutoff_margin
         # tasks.py:82-84: workspace boundaries scaled by 1.08
         self.ws_min = torch.tensor(ws_limits[0], dtype=torch.float32) * 1.08
         self.ws_max = torch.tensor(ws_limits[1], dtype=torch.float32) * 1.08

@@ -1,0 +1,232 @@
+"""-m gpu parity tests: mmd_b200 (CUDA, through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances: fp32 UNet (FFMA accumulation order differs from oneDNN) 2e-5 relative per forward; guide gradients 1e-5
+absolute (they are clipped to unit norm); whole chains 1e-3 relative L2 per trajectory (north star) -- measured values
+are printed.  Integer outputs (cell indices, rr collisions, free masks) are compared bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import port
+from tests.helpers import (LIMITS, build_oracle, build_product, max_err, random_constraints, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair(dev):
+    o = build_oracle("EnvHighways2D", T=25)
+    p = build_product(dev, "EnvHighways2D", T=25, P=o["P"])
+    return o, p
+
+
+def test_cond_table_matches_time_mlp(pair, dev):
+    import ctypes as C
+    from mmd_b200 import _lib
+    o, p = pair
+    P = o["P"]
+    import torch.nn.functional as F
+    for t in (0, 7, 24):
+        temb = port.sinusoidal_pos_emb(torch.tensor([float(t)]))
+        temb = F.linear(temb, P["time_mlp.encoder.1.weight"], P["time_mlp.encoder.1.bias"])
+        temb = F.linear(F.mish(temb), P["time_mlp.encoder.3.weight"], P["time_mlp.encoder.3.bias"])
+        ref = F.linear(F.mish(temb), P["downs.0.0.cond_mlp.1.weight"], P["downs.0.0.cond_mlp.1.bias"])[0]
+        n = C.c_int()
+        h = p["unet"].native()
+        _lib.check(_lib.lib().mmdk_unet_cond_row(h, t, None, C.byref(n), _lib.stream_ptr()))
+        row = torch.empty(n.value, device=dev)
+        _lib.check(_lib.lib().mmdk_unet_cond_row(h, t, _lib.ptr(row), C.byref(n), _lib.stream_ptr()))
+        assert max_err(row[:32], ref) < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 5, 7])
+def test_unet_fp32_matches_oracle(pair, dev, B):
+    o, p = pair
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 64, 4, generator=g)
+    for t in (0, 11, 24):
+        ref = port.unet_forward(o["P"], x, torch.full((B,), t, dtype=torch.long))
+        out = p["unet"].forward_t(x.to(dev), t, precision="fp32")
+        e = rel_err(out, ref)
+        print(f"unet fp32 B={B} t={t} rel_err={e:.3e}")
+        assert e < 2e-5
+
+
+def test_unet_dim_mults_option1(dev):
+    o = build_oracle("EnvEmpty2D", T=10, dim_mults=(1, 2, 4, 8))
+    p = build_product(dev, "EnvEmpty2D", T=10, P=o["P"], dim_mults=(1, 2, 4, 8))
+    x = torch.randn(3, 64, 4, generator=torch.Generator().manual_seed(3))
+    ref = port.unet_forward(o["P"], x, torch.full((3,), 4, dtype=torch.long))
+    out = p["unet"].forward_t(x.to(dev), 4)
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_cell_index_bit_exact(pair, dev):
+    import ctypes as C
+    from mmd_b200 import _lib
+    o, p = pair
+    g = torch.Generator().manual_seed(1)
+    pts = torch.rand(20000, 2, generator=g) * 2.4 - 1.2  # includes out-of-bounds
+    edges = (torch.arange(0, 401).float() / 400 * 2 - 1)  # points straddling cell edges
+    e2 = torch.stack((edges, edges.flip(0)), -1)
+    pts = torch.cat((pts, e2, torch.nextafter(e2, torch.tensor(2.0)), torch.nextafter(e2, torch.tensor(-2.0))))
+    ref = o["guide"].grid.cell_index(pts)
+    env, keep = p["guide"].lower_env(dev)
+    out = torch.empty(pts.shape[0], 2, dtype=torch.int32, device=dev)
+    pd = pts.to(dev).contiguous()
+    _lib.check(_lib.lib().mmdk_cell_index(C.byref(env), _lib.ptr(pd), pts.shape[0], _lib.ptr(out), _lib.stream_ptr()))
+    assert torch.equal(out.cpu(), ref.to(torch.int32))
+
+
+@pytest.mark.parametrize("K,scale", [(16, 0.4), (16, 0.9), (40, 0.5), (128, 0.45)])
+def test_guide_grad_matches_oracle(pair, dev, K, scale):
+    """One GuideManager.forward evaluation incl. extra CostConstraint objects; scale 0.9 makes the global clip fire,
+    K=40/128 exercises the cluster (DSMEM flag exchange) path."""
+    import mmd_b200 as M
+    o, p = pair
+    g = torch.Generator().manual_seed(K)
+    x = torch.randn(K, 64, 4, generator=g) * scale
+    qs, rng, rad = random_constraints(200, seed=K)
+    hard_q, hard_rng, hard_rad = torch.tensor([[0.1, 0.2]]), torch.tensor([[10., 15.]]), torch.tensor([0.12])
+    o["guide"].extra = [port.Constraint(qs, rng, rad, True), port.Constraint(hard_q, hard_rng, hard_rad, False)]
+    ref, parts = o["guide"](x, return_parts=True)
+    o["guide"].extra = []
+    ta = p["ta"]
+    cc = [M.CostConstraint(p["robot"], 64, q_l=list(qs), traj_range_l=rng.tolist(), radius_l=rad.tolist(),
+                           is_soft=True, tensor_args=ta),
+          M.CostConstraint(p["robot"], 64, q_l=list(hard_q), traj_range_l=hard_rng.tolist(), radius_l=hard_rad.tolist(),
+                           is_soft=False, tensor_args=ta)]
+    p["guide"].add_extra_costs(cc, [2e-2, 2e-1])
+    try:
+        out, raw = p["guide"](x.to(dev), return_raw=True)
+    finally:
+        p["guide"].reset_extra_costs()
+    for k, (g_raw, _) in enumerate(parts):
+        scale_k = float(g_raw.abs().max()) + 1e-12
+        assert max_err(raw[k], g_raw) / scale_k < 2e-5, f"raw gradient of cost {k}"
+    e = max_err(out, ref)
+    print(f"guide K={K} scale={scale} max_abs_err={e:.3e} (|grad| max {float(ref.abs().max()):.3f})")
+    assert e < 1e-6
+
+
+@pytest.mark.parametrize("env_name", ["EnvEmpty2D", "EnvConveyor2D", "EnvDropRegion2D"])
+def test_guide_other_envs(dev, env_name):
+    o = build_oracle(env_name, T=5)
+    p = build_product(dev, env_name, T=5, P=o["P"])
+    x = torch.randn(12, 64, 4, generator=torch.Generator().manual_seed(5)) * 0.5
+    assert max_err(p["guide"](x.to(dev)), o["guide"](x)) < 1e-6
+
+
+def test_guide_gradient_steps_block(pair, dev):
+    """20 fused guide steps (sample_functions.py:89-107)."""
+    import mmd_b200 as M
+    o, p = pair
+    x = torch.randn(16, 64, 4, generator=torch.Generator().manual_seed(9)) * 0.5
+    hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, 0.0]), torch.tensor([0.8, 0.1]), o["norm"])
+    ref = port.guide_gradient_steps(x.clone(), port.repeat_hard_conds(hc, 16), o["guide"], 20)
+    out = M.guide_gradient_steps(x.to(dev), {k: v.to(dev) for k, v in hc.items()}, p["guide"], 20)
+    e = rel_err(out, ref)
+    print(f"20 guide steps rel_err={e:.3e}")
+    assert e < 1e-5
+
+
+@pytest.mark.parametrize("K,T,out_scale", [(8, 25, 1.0), (8, 25, 0.05), (24, 10, 1.0)])
+def test_run_inference_chain(dev, K, T, out_scale):
+    """Full reverse chain through GaussianDiffusionModel.run_inference with the oracle's noise."""
+    import mmd_b200 as M
+    o = build_oracle("EnvHighways2D", T=T, out_scale=out_scale)
+    p = build_product(dev, "EnvHighways2D", T=T, P=o["P"])
+    noise = torch.randn(T + 2, K, 64, 4, generator=torch.Generator().manual_seed(18))
+    hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, 0.0]), torch.tensor([0.8, 0.1]), o["norm"])
+    qs, rng, rad = random_constraints(120, seed=3)
+    o["guide"].extra = [port.Constraint(qs, rng, rad, True)]
+    ref = port.run_inference(o["model"], hc, K, noise, guide=o["guide"])
+    o["guide"].extra = []
+    cc = M.CostConstraint(p["robot"], 64, q_l=list(qs), traj_range_l=rng.tolist(), radius_l=rad.tolist(), is_soft=True,
+                          tensor_args=p["ta"])
+    p["guide"].add_extra_costs([cc], [2e-2])
+    try:
+        chain = p["model"].run_inference(None, {k: v.to(dev) for k, v in hc.items()}, n_samples=K, horizon=64,
+                                         return_chain=True, sample_fn=M.ddpm_sample_fn, guide=p["guide"],
+                                         n_guide_steps=20, t_start_guide=math.ceil(0.5 * T),
+                                         noise_std_extra_schedule_fn=lambda x: 0.5,
+                                         n_diffusion_steps_without_noise=1, noise=noise.to(dev))
+    finally:
+        p["guide"].reset_extra_costs()
+    assert chain.shape == ref.shape
+    per_traj = ((chain[-1].cpu() - ref[-1]).flatten(1).norm(dim=1) / ref[-1].flatten(1).norm(dim=1))
+    print(f"chain K={K} T={T} out_scale={out_scale}: final rel L2 max={float(per_traj.max()):.3e} "
+          f"median={float(per_traj.median()):.3e}; whole chain rel={rel_err(chain, ref):.3e}")
+    assert float(per_traj.max()) < 1e-3
+
+
+def test_run_local_inference(dev):
+    import mmd_b200 as M
+    T, K = 25, 8
+    o = build_oracle("EnvConveyor2D", T=T)
+    p = build_product(dev, "EnvConveyor2D", T=T, P=o["P"])
+    g = torch.Generator().manual_seed(4)
+    seed = torch.randn(K, 64, 4, generator=g) * 0.3
+    noise = torch.randn(3 + 2, K, 64, 4, generator=g)
+    hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, -0.6]), torch.tensor([0.8, 0.6]), o["norm"])
+    ref = port.run_local_inference(o["model"], seed, 3, 3, hc, K, noise, guide=o["guide"])
+    out = p["model"].run_local_inference(seed.to(dev), 3, 3, None, {k: v.to(dev) for k, v in hc.items()}, n_samples=K,
+                                         horizon=64, return_chain=True, sample_fn=M.ddpm_sample_fn, guide=p["guide"],
+                                         n_guide_steps=20, t_start_guide=math.ceil(0.5 * T),
+                                         noise_std_extra_schedule_fn=lambda x: 0.5, n_diffusion_steps_without_noise=1,
+                                         noise=noise.to(dev))
+    assert out.shape == ref.shape
+    assert rel_err(out[-1], ref[-1]) < 1e-4
+
+
+def test_lockstep_matches_oracle(dev):
+    import mmd_b200 as M
+    R, K, T = 3, 4, 10
+    o = build_oracle("EnvEmpty2D", T=T)
+    p = build_product(dev, "EnvEmpty2D", T=T, P=o["P"])
+    starts, goals = port.get_start_goal_pos_circle(R, 0.3)  # close together so the peer term is active
+    hcs = [port.hard_conds_from_start_goal(s, g, o["norm"]) for s, g in zip(starts, goals)]
+    noise = torch.randn(R, T + 2, K, 64, 4, generator=torch.Generator().manual_seed(7))
+    guides = [port.GuideSpec(o["guide"].grid, o["norm"]) for _ in range(R)]
+    ref = port.lockstep_sample(o["model"], guides, hcs, K, noise)
+    smp = M.MultiRobotSampler(p["model"], p["guide"])
+    out = smp.sample([{k: v for k, v in hc.items()} for hc in hcs], K, noise=noise.to(dev), mode="lockstep")
+    e = rel_err(out, ref)
+    print(f"lockstep R={R} K={K} T={T} rel_err={e:.3e}")
+    assert e < 1e-3
+
+
+def test_check_rr_collisions_bit_exact(pair, dev):
+    o, p = pair
+    g = torch.Generator().manual_seed(2)
+    pos = torch.rand(64, 12, 2, generator=g) * 0.6 - 0.3
+    # adversarial pairs on a dyadic lattice around the 0.105 threshold (exact squares -> unambiguous in fp32)
+    lat = torch.arange(0, 12).float() * (27.0 / 256.0)  # 0.10546875 spacing: just above 2.1 r
+    pos[0, :, 0], pos[0, :, 1] = lat, 0.0
+    pos[1, :, 0], pos[1, :, 1] = lat * (26.0 / 27.0), 0.0  # 0.1015625 spacing: just below
+    ref_c, ref_m = port.check_rr_collisions(pos)
+    out_c, out_m = p["robot"].check_rr_collisions(pos.to(dev))
+    assert torch.equal(out_c.cpu(), ref_c)
+    assert torch.equal(torch.isnan(out_m.cpu()), torch.isnan(ref_m))
+    assert torch.equal(torch.nan_to_num(out_m.cpu()), torch.nan_to_num(ref_m))
+
+
+def test_classify_trajs_matches_oracle(pair, dev):
+    o, p = pair
+    g = torch.Generator().manual_seed(6)
+    K = 96
+    t = torch.linspace(0, 1, 64)[None, :, None]
+    a = torch.rand(K, 1, 2, generator=g) * 1.8 - 0.9
+    b = torch.rand(K, 1, 2, generator=g) * 1.8 - 0.9
+    pos = a * (1 - t) + b * t + 0.02 * torch.randn(K, 64, 2, generator=g)
+    pos[:5] *= 1.3  # some leave the joint limits
+    trajs = torch.cat((pos, 0.1 * torch.randn(K, 64, 2, generator=g)), -1)
+    free_idx, coll = port.get_trajs_free_idxs(trajs, o["guide"].grid)
+    free, cost, wp = p["task"].classify(trajs.to(dev), return_waypoints=True)
+    assert torch.equal(wp.cpu().bool(), coll)
+    assert torch.equal(torch.argwhere(free.cpu().bool()).reshape(-1), free_idx)
+    ref_cost = port.compute_path_length(trajs) + port.compute_smoothness(trajs)
+    assert rel_err(cost, ref_cost) < 1e-5
+    assert 0 < free_idx.numel() < K
