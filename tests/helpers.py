@@ -8,17 +8,18 @@ from oracle import port
 LIMITS = port.DEFAULT_NORMALIZER_LIMITS
 
 
-def build_oracle(env_name="EnvHighways2D", T=25, seed=0, out_scale=1.0, dim_mults=(1, 2, 4), cutoff_margin=0.05):
+def build_oracle(env_name="EnvHighways2D", T=25, seed=0, out_scale=1.0, dim_mults=(1, 2, 4), cutoff_margin=0.05,
+                 w_smooth=8e-2):
     P = port.make_unet_params(seed=seed, out_scale=out_scale, dim_mults=dim_mults)
     sdf, grad = port.build_sdf_grid(env_name)
     norm = port.LimitsNormalizer(*LIMITS)
-    guide = port.GuideSpec(port.GridSDF(sdf, grad), norm, cutoff_margin=cutoff_margin)
+    guide = port.GuideSpec(port.GridSDF(sdf, grad), norm, cutoff_margin=cutoff_margin, w_smooth=w_smooth)
     model = port.DiffusionModel(P, T)
     return dict(P=P, guide=guide, model=model, norm=norm, sdf=sdf, grad=grad)
 
 
 def build_product(dev, env_name="EnvHighways2D", T=25, P=None, dim_mults=(1, 2, 4), cutoff_margin=0.05,
-                  precision="fp32"):
+                  precision="fp32", w_smooth=8e-2):
     import mmd_b200 as M
     ta = {"device": dev, "dtype": torch.float32}
     env = M.envs.get_env(env_name + "ExtraObjects", tensor_args=ta)
@@ -37,7 +38,7 @@ def build_product(dev, env_name="EnvHighways2D", T=25, P=None, dim_mults=(1, 2, 
         costs.append(M.CostCollision(robot, 64, field=field, sigma_coll=1.0, tensor_args=ta))
         weights.append(2e-2)
     costs.append(M.CostGPTrajectory(robot, 64, dt, sigma_gp=1.0, tensor_args=ta))
-    weights.append(8e-2)
+    weights.append(w_smooth)
     comp = M.CostComposite(robot, 64, costs, weights_cost_l=weights, tensor_args=ta)
     guide = M.GuideManagerTrajectoriesWithVelocity(dataset, comp, clip_grad=True,
                                                    interpolate_trajectories_for_collision=True,

