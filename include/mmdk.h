@@ -69,8 +69,7 @@ void mmdk_unet_destroy(mmdk_unet* net);
 
 /* Numerical mode of the conv contractions. */
 #define MMDK_UNET_FP32 0     /* CUDA-core FFMA, fp32 throughout (exact-parity mode) */
-#define MMDK_UNET_TF32 1     /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
-#define MMDK_UNET_TF32X3 2   /* tcgen05 3xTF32 error-compensated split */
+#define MMDK_UNET_F16X3 1    /* tcgen05 kind::f16, operands split hi+lo in FP16 (3 MMAs), fp32 accumulate in TMEM */
 
 /* eps = TemporalUnet.forward(x, t, context=None) for an integer timestep t shared by the batch
  * (temporal_unet.py:121-174; make_timesteps, diffusion_model_base.py:27-29).  x_dev, eps_dev: [B, H, D]. */
@@ -78,6 +77,12 @@ int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B,
 
 /* Debug/parity tap: copies the precomputed cond table row of timestep t ([n_cond] floats) to out_dev. */
 int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond, void* stream);
+
+/* Debug/parity tap of the tensor-core executor: activation written by op `op_index` of the layer program (-1 = the
+ * packed network input) during the LAST MMDK_UNET_F16X3 forward, as fp32 [B, C, L].  C/L are returned through
+ * c_out/l_out; pass out_dev = NULL to query them.  n_ops_out (optional) receives the number of ops. */
+int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int* c_out, int* l_out, int* n_ops_out,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Guide + DDPM step  (mmd/models/diffusion_models/guides.py:152-253, sample_functions.py:41-107,

@@ -70,8 +70,7 @@ int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B,
   if (B <= 0) return MMDK_OK;
   if (t < 0 || t >= net->impl->cfg.n_diffusion_steps) return fail(MMDK_EINVAL, "timestep out of range");
   if (mode == MMDK_UNET_FP32) return unet_forward_ffma(net->impl, x_dev, B, t, eps_dev, (cudaStream_t)stream);
-  if (mode == MMDK_UNET_TF32 || mode == MMDK_UNET_TF32X3)
-    return unet_forward_tc(net->impl, mode, x_dev, B, t, eps_dev, (cudaStream_t)stream);
+  if (mode == MMDK_UNET_F16X3) return unet_forward_tc(net->impl, mode, x_dev, B, t, eps_dev, (cudaStream_t)stream);
   return fail(MMDK_EINVAL, "unknown UNet mode");
 }
 
@@ -83,6 +82,13 @@ int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond,
   int n = net->impl->n_cond;
   copy_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(net->impl->cond_table + (size_t)t * n, out_dev, n);
   return check_cuda(cudaGetLastError(), "copy_kernel");
+}
+
+int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int* c_out, int* l_out, int* n_ops_out,
+                        void* stream) {
+  if (!net) return fail(MMDK_EINVAL, "null argument");
+  if (n_ops_out) *n_ops_out = (int)net->impl->ops.size();
+  return unet_tc_tap(net->impl, op_index, out_dev, c_out, l_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

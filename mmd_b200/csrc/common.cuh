@@ -41,6 +41,11 @@ struct Op {
   int res_src;   // residual input buffer offset or -1
   int res_cin;   // channels of the residual input
   int res_w, res_b;  // 1x1 residual conv [cin][cout] or -1 (identity)
+  // dataflow for executors that keep activations outside shared memory: index of the op producing each input
+  // (-1 = the network input x); p_src1 = second half of a channel concat (temporal_unet.py:162) or -2 if none
+  int p_src0, p_src1, p_res, p_res1;
+  int c_src0;        // channels coming from p_src0 (cin - c_src0 come from p_src1)
+  int c_res0;        // channels of the residual input coming from p_res (res_cin - c_res0 from p_res1)
 };
 
 static constexpr int kMaxOps = 64;

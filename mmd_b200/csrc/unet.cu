@@ -346,6 +346,24 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
   n_cond = 0;
   ops.clear();
   conds.clear();
+  std::map<int, int> prod;   // activation buffer offset -> index of the op that last wrote it (-1: network input)
+  prod[R[0]] = -1;
+  auto wire = [&](Op& o, int pitch) {
+    o.p_src0 = prod.count(o.src) ? prod[o.src] : -1;
+    o.p_src1 = -2;
+    o.c_src0 = o.cin;
+    if (o.p_src0 >= 0 && ops[o.p_src0].cout < o.cin) {   // channel concat: second producer wrote the upper half
+      o.c_src0 = ops[o.p_src0].cout;
+      o.p_src1 = prod[o.src + o.c_src0 * pitch];
+    }
+    o.p_res = (o.res_src >= 0) ? (prod.count(o.res_src) ? prod[o.res_src] : -1) : -2;
+    o.p_res1 = -2;
+    o.c_res0 = o.res_cin;
+    if (o.p_res >= 0 && ops[o.p_res].cout < o.res_cin) {
+      o.c_res0 = ops[o.p_res].cout;
+      o.p_res1 = prod[o.res_src + o.c_res0 * pitch];
+    }
+  };
 
   auto convblock = [&](const std::string& pre, int cin, int cout, int len, int src, int dst, int cond_off, int res_src,
                        int res_cin, const std::string& res_key) -> bool {
@@ -361,6 +379,8 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
       o.res_w = bld.conv(res_key + ".weight", res_cin, cout, 1, false);
       o.res_b = bld.vec(res_key + ".bias", cout);
     }
+    wire(o, len + 4);
+    prod[dst] = (int)ops.size();
     ops.push_back(o);
     return bld.err.empty();
   };
@@ -395,6 +415,9 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
       o.src = cur; o.dst = other(cur, -1);
       o.w = bld.conv(p + ".4.conv.weight", dims[i + 1], dims[i + 1], 3, false);
       o.b = bld.vec(p + ".4.conv.bias", dims[i + 1]);
+      o.res_src = -1;
+      wire(o, L[i] + 4);
+      prod[o.dst] = (int)ops.size();
       ops.push_back(o);
       cur = o.dst;
     }
@@ -428,6 +451,9 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
     o.dst = (lvl - 1 >= 1) ? cat[lvl - 1] : other(cur, -1);
     o.w = bld.conv(p + ".4.conv.weight", cmid, cmid, 4, true);
     o.b = bld.vec(p + ".4.conv.bias", cmid);
+    o.res_src = -1;
+    wire(o, L[lvl] + 4);
+    prod[o.dst] = (int)ops.size();
     ops.push_back(o);
     cur = o.dst;
   }
@@ -440,6 +466,8 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
     o.src = t1; o.dst = 0;
     o.w = bld.conv("final_conv.1.weight", cfg.unet_input_dim, cfg.state_dim, 1, false);
     o.b = bld.vec("final_conv.1.bias", cfg.state_dim);
+    o.res_src = -1;
+    wire(o, cfg.horizon + 4);
     ops.push_back(o);
   }
   if (!bld.err.empty()) return MMDK_EINVAL;

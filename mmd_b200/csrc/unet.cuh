@@ -28,5 +28,6 @@ int unet_forward_ffma(const UnetImpl* net, const float* x, int B, int t, float* 
 // tcgen05 executor (unet_tc.cu)
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream);
 void unet_tc_release(UnetImpl* net);
+int unet_tc_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out, cudaStream_t stream);
 
 }  // namespace mmdk

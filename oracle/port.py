@@ -196,14 +196,18 @@ def group_norm_n_groups(n_channels, target=8):  # layers.py:392-398
     return 1
 
 
-def _rtb(p, pre, x, c):  # layers.py:346-358
+def _rtb(p, pre, x, c, ops=None):  # layers.py:346-358
     h = _conv1d_block(p, pre + ".blocks.0", x)
     h = h + F.linear(F.mish(c), p[pre + ".cond_mlp.1.weight"], p[pre + ".cond_mlp.1.bias"])[:, :, None]
+    if ops is not None:
+        ops.append((pre + ".blocks.0", h))
     h = _conv1d_block(p, pre + ".blocks.1", h)
     if pre + ".residual_conv.weight" in p:
         res = F.conv1d(x, p[pre + ".residual_conv.weight"], p[pre + ".residual_conv.bias"])
     else:
         res = x
+    if ops is not None:
+        ops.append((pre + ".blocks.1", h + res))
     return h + res
 
 
@@ -230,32 +234,41 @@ def unet_forward(p: Dict[str, torch.Tensor], x, t, taps: Optional[dict] = None):
     attn = any(".fn.fn.to_qkv." in k for k in p)
     x = x.transpose(1, 2)
     hs = []
+    ops = None  # per-op activations in layer-program order (debug taps of the executors)
+    if taps is not None:
+        ops = taps.setdefault("ops", [])
     for i in range(n_levels):
-        x = _rtb(p, f"downs.{i}.0", x, temb)
-        x = _rtb(p, f"downs.{i}.1", x, temb)
+        x = _rtb(p, f"downs.{i}.0", x, temb, ops)
+        x = _rtb(p, f"downs.{i}.1", x, temb, ops)
         if attn:
             x = _linear_attention(p, f"downs.{i}.2", x)
         hs.append(x)
         if i < n_levels - 1:
             x = F.conv1d(x, p[f"downs.{i}.4.conv.weight"], p[f"downs.{i}.4.conv.bias"], stride=2, padding=1)
+            if ops is not None:
+                ops.append((f"downs.{i}.4", x))
         if taps is not None:
             taps[f"down{i}"] = x
-    x = _rtb(p, "mid_block1", x, temb)
+    x = _rtb(p, "mid_block1", x, temb, ops)
     if attn:
         x = _linear_attention(p, "mid_attn", x)
-    x = _rtb(p, "mid_block2", x, temb)
+    x = _rtb(p, "mid_block2", x, temb, ops)
     if taps is not None:
         taps["mid"] = x
     for i in range(n_levels - 1):
         x = torch.cat((x, hs.pop()), dim=1)
-        x = _rtb(p, f"ups.{i}.0", x, temb)
-        x = _rtb(p, f"ups.{i}.1", x, temb)
+        x = _rtb(p, f"ups.{i}.0", x, temb, ops)
+        x = _rtb(p, f"ups.{i}.1", x, temb, ops)
         if attn:
             x = _linear_attention(p, f"ups.{i}.2", x)
         x = F.conv_transpose1d(x, p[f"ups.{i}.4.conv.weight"], p[f"ups.{i}.4.conv.bias"], stride=2, padding=1)
+        if ops is not None:
+            ops.append((f"ups.{i}.4", x))
         if taps is not None:
             taps[f"up{i}"] = x
     x = _conv1d_block(p, "final_conv.0", x)
+    if ops is not None:
+        ops.append(("final_conv.0", x))
     x = F.conv1d(x, p["final_conv.1.weight"], p["final_conv.1.bias"])
     return x.transpose(1, 2)
 

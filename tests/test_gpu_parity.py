@@ -54,6 +54,35 @@ def test_unet_fp32_matches_oracle(pair, dev, B):
         assert e < 2e-5
 
 
+@pytest.mark.parametrize("B", [3, 7, 20])
+def test_unet_tensor_core_matches_oracle(pair, dev, B):
+    """tcgen05 executor (FP16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM): every layer op through the debug tap,
+    then eps.  Expected ~2e-6 (CPU emulation of the operand format); bar 5e-5."""
+    import ctypes as C
+    from mmd_b200 import _lib
+    o, p = pair
+    x = torch.randn(B, 64, 4, generator=torch.Generator().manual_seed(100 + B))
+    for t in (3, 24):
+        taps = {}
+        ref = port.unet_forward(o["P"], x, torch.full((B,), t, dtype=torch.long), taps=taps)
+        out = p["unet"].forward_t(x.to(dev), t, precision="f16x3")
+        torch.cuda.synchronize()
+        h = p["unet"].native()
+        worst = 0.0
+        for j, (name, act) in enumerate(taps["ops"]):
+            c, l = C.c_int(), C.c_int()
+            _lib.check(_lib.lib().mmdk_unet_debug_tap(h, j, None, C.byref(c), C.byref(l), None, _lib.stream_ptr()))
+            assert (c.value, l.value) == (act.shape[1], act.shape[2]), name
+            buf = torch.empty(B, c.value, l.value, device=dev)
+            _lib.check(_lib.lib().mmdk_unet_debug_tap(h, j, _lib.ptr(buf), C.byref(c), C.byref(l), None, _lib.stream_ptr()))
+            e = rel_err(buf, act)
+            worst = max(worst, e)
+            assert e < 5e-5, f"op {j} ({name}) rel_err {e:.3e}"
+        e = rel_err(out, ref)
+        print(f"unet f16x3 B={B} t={t}: eps rel_err={e:.3e}, worst layer {worst:.3e}")
+        assert e < 5e-5
+
+
 def test_unet_dim_mults_option1(dev):
     o = build_oracle("EnvEmpty2D", T=25, dim_mults=(1, 2, 4, 8))
     p = build_product(dev, "EnvEmpty2D", T=25, P=o["P"], dim_mults=(1, 2, 4, 8))
