@@ -29,8 +29,8 @@ namespace mmdk {
 namespace {
 
 constexpr int ST = 7;          // samples per tile
-constexpr int W_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int MAX_W_STAGES = 3;
+constexpr int TC_THREADS = 320;
 constexpr int TMEM_COLS = 256;
 constexpr int MAX_SRC = 4;
 
@@ -58,6 +58,7 @@ struct TcOpParams {
   const ChunkDesc* chunks;
   int n_chunks;
   uint32_t w_stage_bytes;
+  int w_stages;
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -137,8 +138,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ float mish_fast(float y) {
   float e = __expf(y);
@@ -173,28 +182,34 @@ __device__ __forceinline__ void add8(const uint4& hi, const uint4& lo, float* y)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// the layer kernel.  NV = accumulator values per thread and region (n_mt * N), N = columns per m-tile.
+// the layer kernel.  NV = accumulator values per image row and region (n_mt * N), N = columns per m-tile.
+// Warps 0-7: epilogue (warp w owns TMEM lanes 32*(w&3).. and the column half w>>2), warp 8: TMEM alloc + MMA issue,
+// warp 9: bulk-copy producer.  __launch_bounds__(320, 2): two CTAs per SM so that one CTA's epilogue (CUDA cores)
+// overlaps the other's loads + MMAs (tensor pipe).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NV, int N>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NMT = NV / N;
+  constexpr int NH = (N >= 32) ? N / 2 : N;      // columns per thread and m-tile
+  constexpr int NVH = NMT * NH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + p.smem_bar_off;
   // barriers: [0] in_full, [1..3] w_full, [4..6] w_empty, [7] acc_full ; then the TMEM base pointer
-  const uint32_t bar_in = bar_base, bar_wfull = bar_base + 8, bar_wempty = bar_base + 8 + 8 * W_STAGES,
-                 bar_acc = bar_base + 8 + 16 * W_STAGES;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + p.smem_bar_off + 8 + 16 * W_STAGES + 8);
+  const uint32_t bar_in = bar_base, bar_wfull = bar_base + 8, bar_wempty = bar_base + 8 + 8 * MAX_W_STAGES,
+                 bar_acc = bar_base + 8 + 16 * MAX_W_STAGES;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + p.smem_bar_off + 8 + 16 * MAX_W_STAGES + 8);
+  const int WS = p.w_stages;
 
   if (tid == 0) {
     mbar_init(bar_in, 1);
-    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+    for (int s = 0; s < MAX_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
                  "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ================= producer: input images, then the weight ring =================
     if (lane == 0) {
       uint32_t total = 0;
@@ -219,24 +234,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams
           off += n;
         }
       }
+      int st = 0, ph = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
-        const int st = c % W_STAGES;
-        mbar_wait(bar_wempty + 8 * st, ((c / W_STAGES) & 1) ^ 1);
+        mbar_wait(bar_wempty + 8 * st, ph ^ 1);
         const ChunkDesc cd = p.chunks[c];
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
         bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        if (++st == WS) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       // instruction descriptor: D fp32 (bit 4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_in, 0);
+      int st = 0, ph = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
-        const int st = c % W_STAGES;
         const ChunkDesc cd = p.chunks[c];
-        mbar_wait(bar_wfull + 8 * st, (c / W_STAGES) & 1);
+        mbar_wait(bar_wfull + 8 * st, ph);
         tc_fence_after();
         const uint32_t wbase = smem_base + p.smem_w_off + st * p.w_stage_bytes;
         const uint32_t b_plane = (uint32_t)cd.k16 * 2u * N * 16u;   // (CK/8) panels * N rows * 16 B
@@ -254,124 +270,136 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams
           }
         }
         tc_commit(bar_wempty + 8 * st);   // frees the weight stage once these MMAs have read it
+        if (++st == WS) { st = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);
     }
   } else {
-    // ================= epilogue: 4 warps, thread = TMEM lane = image row =================
-    float* scratch = reinterpret_cast<float*>(smem + p.smem_scratch_off);  // [NMT*128][8] partials, then stats
-    float* stat_mean = scratch + NMT * 128 * 8;                              // [ST][8]
+    // ================= epilogue: 8 warps; thread = (TMEM lane = image row, column half) =================
+    float* prm = reinterpret_cast<float*>(smem + p.smem_scratch_off);   // bias | gamma | beta | cond | res_bias, N each
+    float2* part = reinterpret_cast<float2*>(prm + 5 * N);              // [NMT*128][8] (sum, M2) per row and group
+    float* stat_mean = reinterpret_cast<float*>(part + NMT * 128 * 8);  // [ST][8]
     float* stat_rstd = stat_mean + ST * 8;
     const int P = p.P, L = p.L;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-
+    const int q4 = warp & 3, half = (N >= 32) ? (warp >> 2) : 0;
+    const bool active = (N >= 32) || (warp < 4);
+    const int row = q4 * 32 + lane;
+    const int c0 = half * NH;                                            // first column of this thread inside an m-tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    // stage the per-channel parameters while the MMAs run
+    if (tid < N) {
+      prm[tid] = (tid < p.cout) ? __ldg(p.bias + tid) : 0.f;
+      prm[N + tid] = p.gamma ? __ldg(p.gamma + tid) : 1.f;
+      prm[2 * N + tid] = p.beta ? __ldg(p.beta + tid) : 0.f;
+      prm[3 * N + tid] = p.cond ? __ldg(p.cond + tid) : 0.f;
+      prm[4 * N + tid] = p.res_bias ? __ldg(p.res_bias + tid) : 0.f;
+    }
     int rs[NMT], rp[NMT];
     bool rvalid[NMT];
 #pragma unroll
     for (int i = 0; i < NMT; ++i) {
-      const int q = 128 * i + tid;
+      const int q = 128 * i + row;
       rs[i] = q / P;
       rp[i] = q - rs[i] * P;
       rvalid[i] = (rs[i] < ST) && (rp[i] < L) && (tile * ST + rs[i] < p.B);
     }
+    epi_bar();
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
 
     const int n_regions = (p.kind == TC_UP) ? 2 : 1;
     for (int region = 0; region < n_regions; ++region) {
-      float v[NV];
+      float v[NVH];
+      if (active) {
 #pragma unroll
-      for (int i = 0; i < NMT; ++i) {
-        if constexpr (N >= 32) {
+        for (int i = 0; i < NMT; ++i) {
+          if constexpr (NH >= 32) {
 #pragma unroll
-          for (int j = 0; j < N / 32; ++j) tmem_ld32(lane_base + region * 128 + i * N + j * 32, v + i * N + j * 32);
-        } else {
-          tmem_ld16(lane_base + region * 128 + i * N, v + i * N);
+            for (int j = 0; j < NH / 32; ++j)
+              tmem_ld32(lane_base + region * 128 + i * N + c0 + j * 32, v + i * NH + j * 32);
+          } else {
+            tmem_ld16(lane_base + region * 128 + i * N + c0, v + i * NH);
+          }
         }
-      }
-      tmem_wait_ld();
-      // bias
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < N; ++c) {
-        const float b = (c < p.cout) ? __ldg(p.bias + c) : 0.f;
+        for (int c = 0; c < NH; ++c) {
+          const float b = prm[c0 + c];
 #pragma unroll
-        for (int i = 0; i < NMT; ++i) v[i * N + c] += b;
+          for (int i = 0; i < NMT; ++i) v[i * NH + c] += b;
+        }
       }
 
       if (p.kind == TC_CONVBLOCK) {
         if constexpr (N >= 32) {
-          constexpr int CPG = N / 8;
-          const float inv_n = 1.f / (float)(CPG * L);
-          // ---- GroupNorm pass 1: mean ----
+          constexpr int CPG = N / 8;          // channels per group
+          constexpr int GH = NH / CPG;        // groups per thread (4)
+          // ---- GroupNorm statistics: per-row (sum, M2) -> one exchange -> Chan's combination (stable, 2 barriers)
 #pragma unroll
           for (int i = 0; i < NMT; ++i)
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < GH; ++g) {
               float s = 0.f;
 #pragma unroll
-              for (int c = 0; c < CPG; ++c) s += v[i * N + g * CPG + c];
-              scratch[(i * 128 + tid) * 8 + g] = rvalid[i] ? s : 0.f;
+              for (int c = 0; c < CPG; ++c) s += v[i * NH + g * CPG + c];
+              const float m = s * (1.f / CPG);
+              float m2 = 0.f;
+#pragma unroll
+              for (int c = 0; c < CPG; ++c) { const float d = v[i * NH + g * CPG + c] - m; m2 = fmaf(d, d, m2); }
+              part[(i * 128 + row) * 8 + half * GH + g] = rvalid[i] ? make_float2(s, m2) : make_float2(0.f, 0.f);
             }
           epi_bar();
           if (tid < ST * 8) {
             const int s = tid >> 3, g = tid & 7;
-            float acc = 0.f;
-            for (int pp = 0; pp < L; ++pp) acc += scratch[(s * P + pp) * 8 + g];
-            stat_mean[tid] = acc * inv_n;
-          }
-          epi_bar();
-          // ---- pass 2: centred second moment ----
-#pragma unroll
-          for (int i = 0; i < NMT; ++i)
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float m = rvalid[i] ? stat_mean[rs[i] * 8 + g] : 0.f;
-              float s = 0.f;
-#pragma unroll
-              for (int c = 0; c < CPG; ++c) { const float d = v[i * N + g * CPG + c] - m; s = fmaf(d, d, s); }
-              scratch[(i * 128 + tid) * 8 + g] = rvalid[i] ? s : 0.f;
+            const float inv_n = 1.f / (float)(CPG * L);
+            float sum = 0.f;
+            for (int pp = 0; pp < L; ++pp) sum += part[(s * P + pp) * 8 + g].x;
+            const float mean = sum * inv_n;
+            float m2 = 0.f;
+            for (int pp = 0; pp < L; ++pp) {
+              const float2 e = part[(s * P + pp) * 8 + g];
+              const float d = e.x * (1.f / CPG) - mean;
+              m2 += e.y + (float)CPG * d * d;
             }
-          epi_bar();
-          if (tid < ST * 8) {
-            const int s = tid >> 3, g = tid & 7;
-            float acc = 0.f;
-            for (int pp = 0; pp < L; ++pp) acc += scratch[(s * P + pp) * 8 + g];
-            stat_rstd[tid] = rsqrtf(acc * inv_n + 1e-5f);
+            stat_mean[tid] = mean;
+            stat_rstd[tid] = rsqrtf(m2 * inv_n + 1e-5f);
           }
           epi_bar();
-          // ---- pass 3: normalise, Mish, +cond, +residual, split, store ----
+          // ---- normalise, Mish, +cond, +residual, split, store ----
 #pragma unroll
           for (int i = 0; i < NMT; ++i) {
-            const int r = 2 + 128 * i + tid;
-            float r1[32];
+            const int r = 2 + 128 * i + row;
+            float r1[8];
 #pragma unroll
-            for (int pc = 0; pc < N / 8; ++pc) {
-              if (p.res_bias != nullptr && (pc & 3) == 0) {  // residual 1x1 conv lives in accumulator region 1
-                tmem_ld32(lane_base + 128 + i * N + pc * 8, r1);
+            for (int pc = 0; pc < NH / 8; ++pc) {
+              const int pcg = c0 / 8 + pc;     // global panel index
+              if (p.res_bias != nullptr) {     // residual 1x1 conv lives in accumulator region 1
+                tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, r1);
                 tmem_wait_ld();
               }
               if (rvalid[i]) {
                 float y[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const int c = pc * 8 + e;
+                  const int cl = pc * 8 + e;            // column inside this thread's half
+                  const int c = c0 + cl;                // channel
                   const int g = c / CPG;
-                  float t = (v[i * N + c] - stat_mean[rs[i] * 8 + g]) * stat_rstd[rs[i] * 8 + g];
-                  t = fmaf(t, __ldg(p.gamma + c), __ldg(p.beta + c));
-                  t = mish_fast(t);
-                  if (p.cond) t += __ldg(p.cond + c);
-                  if (p.res_bias) t += r1[(pc & 3) * 8 + e] + __ldg(p.res_bias + c);
+                  const float a = stat_rstd[rs[i] * 8 + g];
+                  float t = (v[i * NH + cl] - stat_mean[rs[i] * 8 + g]) * a;
+                  t = fmaf(t, prm[N + c], prm[2 * N + c]);
+                  t = mish_fast(t) + prm[3 * N + c];
+                  if (p.res_bias) t += r1[e] + prm[4 * N + c];
                   y[e] = t;
                 }
                 if (p.res_id) {
-                  const uint8_t* rb = p.res_id + (size_t)tile * p.res_id_tile_bytes + ((size_t)pc * p.res_id_rows + r) * 16;
-                  const uint4 h = *reinterpret_cast<const uint4*>(rb);
-                  const uint4 l = *reinterpret_cast<const uint4*>(rb + (size_t)(p.res_id_C / 8) * p.res_id_rows * 16);
+                  const uint8_t* rb = p.res_id + (size_t)tile * p.res_id_tile_bytes + ((size_t)pcg * p.res_id_rows + r) * 16;
+                  const uint4 h = __ldg(reinterpret_cast<const uint4*>(rb));
+                  const uint4 l = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(p.res_id_C / 8) * p.res_id_rows * 16));
                   add8(h, l, y);
                 }
                 uint4 hi, lo;
                 split8(y, hi, lo);
-                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)pc * p.out_rows + r) * 16;
+                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)pcg * p.out_rows + r) * 16;
                 *reinterpret_cast<uint4*>(ob) = hi;
                 *reinterpret_cast<uint4*>(ob + (size_t)(p.out_C / 8) * p.out_rows * 16) = lo;
               }
@@ -393,23 +421,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams
             }
             if (ok) {
 #pragma unroll
-              for (int pc = 0; pc < N / 8; ++pc) {
+              for (int pc = 0; pc < NH / 8; ++pc) {
                 uint4 hi, lo;
-                split8(v + i * N + pc * 8, hi, lo);
-                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)pc * p.out_rows + ro) * 16;
+                split8(v + i * NH + pc * 8, hi, lo);
+                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)(c0 / 8 + pc) * p.out_rows + ro) * 16;
                 *reinterpret_cast<uint4*>(ob) = hi;
                 *reinterpret_cast<uint4*>(ob + (size_t)(p.out_C / 8) * p.out_rows * 16) = lo;
               }
             }
           }
         }
-      } else {  // TC_FINAL: eps [B][L][4]
+      } else if (active) {  // TC_FINAL: eps [B][L][4]
 #pragma unroll
         for (int i = 0; i < NMT; ++i) {
           if (rvalid[i]) {
             const size_t b = (size_t)tile * ST + rs[i];
             *reinterpret_cast<float4*>(p.eps + (b * L + rp[i]) * 4) =
-                make_float4(v[i * N + 0], v[i * N + 1], v[i * N + 2], v[i * N + 3]);
+                make_float4(v[i * NH + 0], v[i * NH + 1], v[i * NH + 2], v[i * NH + 3]);
           }
         }
       }
@@ -417,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcOpParams
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -638,12 +666,16 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     p.n_chunks = (int)chunks.size();
     p.w_stage_bytes = (w_stage + 127) & ~127u;
     p.smem_w_off = off;
-    off += W_STAGES * p.w_stage_bytes;
+    const uint32_t scratch = (uint32_t)(5 * p.N + p.n_mt * 128 * 8 * 2 + 2 * ST * 8) * 4;
+    const uint32_t tail = ((scratch + 15) & ~15u) + 8 + 16 * MAX_W_STAGES + 8 + 16;
+    // two CTAs per SM (one's epilogue under the other's MMAs) need <= ~112 KB each: shrink the weight ring if that helps
+    p.w_stages = MAX_W_STAGES;
+    if (off + MAX_W_STAGES * p.w_stage_bytes + tail > 114688u && off + 2 * p.w_stage_bytes + tail <= 114688u) p.w_stages = 2;
+    off += p.w_stages * p.w_stage_bytes;
     p.smem_scratch_off = off;
-    off += (uint32_t)(p.n_mt * 128 * 8 + 2 * ST * 8) * 4;
-    off = (off + 15) & ~15u;
+    off += (scratch + 15) & ~15u;
     p.smem_bar_off = off;
-    off += 8 + 16 * W_STAGES + 8 + 16;
+    off += 8 + 16 * MAX_W_STAGES + 8 + 16;
     h.smem = off;
     if (h.smem > 232448) return fail_free("tensor-core executor: layer does not fit in shared memory");
     // weights + chunk table to the device

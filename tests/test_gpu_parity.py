@@ -280,7 +280,6 @@ def test_lockstep_matches_oracle(dev):
     # from itself by median 2.4e-4 / p90 3.3e-3 / max 5.2e-3 on this very problem.  The bar is
     # that envelope; the per-evaluation arithmetic is pinned exactly by test_peer_term_equals_constraint_object.
     assert float(e.median()) < 1e-3 and float(e.quantile(0.9)) < 1e-2 and float(e.max()) < 5e-2
-    assert e < 1e-3
 
 
 def test_peer_term_equals_constraint_object(pair, dev):
