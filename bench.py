@@ -201,7 +201,7 @@ def run_gpu(args):
 
     n_steps = T + N_EXTRA
     gen = torch.Generator(device=dev).manual_seed(18 + rank)
-    noise = torch.randn(R_PER_GPU, n_steps + 1, K, H, D, device=dev, generator=gen)
+    noise = torch.randn(n_steps + 1, R_PER_GPU * K, H, D, device=dev, generator=gen)  # step-major: one contiguous frame per step
     hcs_dev = hard_conds_from(sg_host.to(dev))
     kw = dict(mode="lockstep", robot_offset=rank * R_PER_GPU, n_robots_total=R_total)
 

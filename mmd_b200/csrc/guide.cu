@@ -223,7 +223,10 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
       for (int e = e0; e < e1; ++e) {
         float4 c = __ldg(reinterpret_cast<const float4*>(a.grp.cons_dev) + e);
         float dx = xu[0] - c.x, dy = xu[1] - c.y;
-        float dist = sqrtf(dx * dx + dy * dy);
+        float d2 = dx * dx + dy * dy;
+        // conservative prefilter: sqrt(d2) > r for sure (the exact reference test below decides the rest)
+        if (d2 > c.z * c.z * 1.0001f) continue;
+        float dist = sqrtf(d2);
         if (!(dist > c.z) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
       }
       emit(gk, a.grp.obj_weight_dev[o]);
@@ -232,11 +235,14 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
     if (a.grp.peers_dev) {
       float gk[4] = {0.f, 0.f, 0.f, 0.f};
       const float r = a.grp.peer_radius;
+      const float r2_far = r * r * 1.0001f;
       for (int j = 0; j < a.grp.n_peers; ++j) {
         if (j == self_peer) continue;
         float2 q = __ldg(reinterpret_cast<const float2*>(a.grp.peers_dev) + (size_t)j * H + h);
         float dx = xu[0] - q.x, dy = xu[1] - q.y;
-        float dist = sqrtf(dx * dx + dy * dy);
+        float d2 = dx * dx + dy * dy;
+        if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
+        float dist = sqrtf(d2);
         if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
       }
       emit(gk, a.grp.peer_weight);

@@ -219,9 +219,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // programmatic dependent launch: everything above (and the weight prefetch below) overlaps the previous layer's
+  // tail; activations written by earlier kernels are only touched after griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 9) {
     // ================= producer: input images, then the weight ring =================
     if (lane == 0) {
+      // weights do not depend on the previous kernel: fill the ring first
+      int st = 0, ph = 0, c_pre = 0;
+      for (; c_pre < p.n_chunks && c_pre < WS; ++c_pre) {
+        const ChunkDesc cd = p.chunks[c_pre];
+        mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
+        bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        if (++st == WS) { st = 0; ph ^= 1; }
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       uint32_t total = 0;
       for (int s = 0; s < p.n_src; ++s) total += p.src_tile_bytes[s];
       mbar_expect_tx(bar_in, total);
@@ -234,8 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
           off += n;
         }
       }
-      int st = 0, ph = 0;
-      for (int c = 0; c < p.n_chunks; ++c) {
+      for (int c = c_pre; c < p.n_chunks; ++c) {
         mbar_wait(bar_wempty + 8 * st, ph ^ 1);
         const ChunkDesc cd = p.chunks[c];
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
@@ -304,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
       rvalid[i] = (rs[i] < ST) && (rp[i] < L) && (tile * ST + rs[i] < p.B);
     }
     epi_bar();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs / residual reads only after the previous grid is complete
     mbar_wait(bar_acc, 0);
     tc_fence_after();
 
@@ -547,8 +559,17 @@ static int launch_tc(const TcOpHost& o, cudaStream_t stream) {
     MMDK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NV, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = 232448;
   }
-  conv_tc_kernel<NV, N><<<o.prm.n_tiles, TC_THREADS, o.smem, stream>>>(o.prm);
-  return check_cuda(cudaGetLastError(), "conv_tc_kernel launch");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)o.prm.n_tiles);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = o.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NV, N>, o.prm), "conv_tc_kernel launch");
 }
 
 static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {

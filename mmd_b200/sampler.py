@@ -38,9 +38,10 @@ class MultiRobotSampler:
     def sample(self, hard_conds_l: Sequence[dict], n_samples: int, noise: Optional[torch.Tensor] = None,
                mode="lockstep", constraints_l=None, return_chain=False, robot_offset=0, n_robots_total=None,
                x_init=None, n_diffusion_steps=None, generator=None):
-        """hard_conds_l: per LOCAL robot {row: state[D]} (normalised).  noise: [R_local, steps+1, K, H, D] or None
-        (drawn with torch.randn on the device).  Returns final [R_local, K, H, D] (and the chain
-        [R_local, steps+1, K, H, D] if return_chain)."""
+        """hard_conds_l: per LOCAL robot {row: state[D]} (normalised).  noise: [R_local, steps+1, K, H, D] (robot-major,
+        the oracle's layout), or step-major [steps+1, R_local*K, H, D] (no per-step gather), or None (drawn with
+        torch.randn on the device).  Returns final [R_local, K, H, D] (and the chain [R_local, steps+1, K, H, D] if
+        return_chain)."""
         lib = _lib.lib()
         model, guide = self.model, self.guide
         dev = model.betas.device
@@ -56,7 +57,8 @@ class MultiRobotSampler:
         if x_init is not None:
             x = x_init.reshape(B, H, D).to(torch.float32).clone().contiguous()
         elif noise is not None:
-            x = noise[:, 0].reshape(B, H, D).to(dev).clone().contiguous()
+            step_major = noise.dim() == 4
+            x = (noise[0] if step_major else noise[:, 0].reshape(B, H, D)).to(dev).clone().contiguous()
         else:
             x = torch.randn(B, H, D, device=dev, generator=generator)
         # hard conditions on x_T (diffusion_model_base.py:195)
@@ -91,7 +93,7 @@ class MultiRobotSampler:
             model.model.forward_t(x, t, precision=model.unet_precision, out=eps)
             sc = model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True)
             if noise is not None:
-                nz = noise[:, k].reshape(B, H, D).to(dev).contiguous()
+                nz = noise[k] if noise.dim() == 4 else noise[:, k].reshape(B, H, D).to(dev).contiguous()
             else:
                 nz = torch.randn(B, H, D, device=dev, generator=generator)
             _lib.check(lib.mmdk_ddpm_step(C.byref(env), C.byref(grp), C.byref(sc), H, _lib.ptr(x), _lib.ptr(eps),
