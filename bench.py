@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mmd_b200", choices=["mmd_b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MMD_UNET_PRECISION", "fp32"), choices=["fp32", "f16x3"])
+    ap.add_argument("--precision", default=os.environ.get("MMD_UNET_PRECISION", "f16x3"), choices=["fp32", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,6 +33,7 @@ constexpr int MAX_W_STAGES = 3;
 constexpr int TC_THREADS = 320;
 constexpr int TMEM_COLS = 256;
 constexpr int MAX_SRC = 4;
+constexpr int MAX_CHUNKS = 48;
 
 struct ChunkDesc {
   uint32_t a_off;    // smem byte offset of the chunk's first A panel (plane hi, buffer row 0)
@@ -55,7 +56,6 @@ struct TcOpParams {
   uint32_t src_smem_off[MAX_SRC];
   int n_src;
   const uint8_t* wchunks;
-  const ChunkDesc* chunks;
   int n_chunks;
   uint32_t w_stage_bytes;
   int w_stages;
@@ -72,6 +72,7 @@ struct TcOpParams {
   int out_L, out_rows, out_C;
   float* eps;
   uint32_t smem_w_off, smem_scratch_off, smem_bar_off;
+  ChunkDesc chunks[MAX_CHUNKS];   // in the kernel parameter (constant) bank: no dependent global loads per chunk
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -93,6 +94,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {   // long waits: do not hog issue slots
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -188,7 +198,7 @@ __device__ __forceinline__ void add8(const uint4& hi, const uint4& lo, float* y)
 // overlaps the other's loads + MMAs (tensor pipe).
 // ------------------------------------------------------------------------------------------------------------------
 template <int NV, int N>
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcOpParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NMT = NV / N;
   constexpr int NH = (N >= 32) ? N / 2 : N;      // columns per thread and m-tile
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
     }
     epi_bar();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs / residual reads only after the previous grid is complete
-    mbar_wait(bar_acc, 0);
+    mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
 
     const int n_regions = (p.kind == TC_UP) ? 2 : 1;
@@ -382,9 +392,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
           for (int i = 0; i < NMT; ++i) {
             const int r = 2 + 128 * i + row;
             float r1[8];
+            // identity residual: issue the (L2-latency) loads of panel pc+1 before the arithmetic of panel pc
+            uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
+            const uint8_t* rbase = p.res_id ? p.res_id + (size_t)tile * p.res_id_tile_bytes + (size_t)r * 16 : nullptr;
+            const size_t rplane = (size_t)(p.res_id_C / 8) * p.res_id_rows * 16;
+            if (rbase && rvalid[i]) {
+              rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16));
+              rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16 + rplane));
+            }
 #pragma unroll
             for (int pc = 0; pc < NH / 8; ++pc) {
               const int pcg = c0 / 8 + pc;     // global panel index
+              const uint4 ch = rh, cl = rl;
+              if (rbase && rvalid[i] && pc + 1 < NH / 8) {
+                rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(pcg + 1) * p.res_id_rows * 16));
+                rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(pcg + 1) * p.res_id_rows * 16 + rplane));
+              }
               if (p.res_bias != nullptr) {     // residual 1x1 conv lives in accumulator region 1
                 tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, r1);
                 tmem_wait_ld();
@@ -403,12 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const TcOpParams
                   if (p.res_bias) t += r1[e] + prm[4 * N + c];
                   y[e] = t;
                 }
-                if (p.res_id) {
-                  const uint8_t* rb = p.res_id + (size_t)tile * p.res_id_tile_bytes + ((size_t)pcg * p.res_id_rows + r) * 16;
-                  const uint4 h = __ldg(reinterpret_cast<const uint4*>(rb));
-                  const uint4 l = __ldg(reinterpret_cast<const uint4*>(rb + (size_t)(p.res_id_C / 8) * p.res_id_rows * 16));
-                  add8(h, l, y);
-                }
+                if (rbase) add8(ch, cl, y);
                 uint4 hi, lo;
                 split8(y, hi, lo);
                 uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)pcg * p.out_rows + r) * 16;
@@ -527,7 +545,6 @@ struct TcOpHost {
   TcOpParams prm{};
   int NV = 0, N = 0;
   size_t smem = 0;
-  ChunkDesc* chunks_dev = nullptr;
   uint8_t* w_dev = nullptr;
   int cond_off = -1;
 };
@@ -544,7 +561,7 @@ static int level_rows(int L) { return 2 + 128 * ((ST * (L + 2) + 127) / 128) + 2
 static void tc_free(TcState* s) {
   if (!s) return;
   for (auto& im : s->images) cudaFree(im.dev);
-  for (auto& o : s->ops) { cudaFree(o.chunks_dev); cudaFree(o.w_dev); }
+  for (auto& o : s->ops) cudaFree(o.w_dev);
   delete s;
 }
 
@@ -700,17 +717,15 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     h.smem = off;
     if (h.smem > 232448) return fail_free("tensor-core executor: layer does not fit in shared memory");
     // weights + chunk table to the device
-    if (cudaMalloc(&h.w_dev, w_total) != cudaSuccess || cudaMalloc(&h.chunks_dev, sizeof(ChunkDesc) * chunks.size()) != cudaSuccess)
-      return fail_free("out of memory (packed weights)");
+    if (chunks.size() > (size_t)MAX_CHUNKS) return fail_free("tensor-core executor: too many weight chunks in one layer");
+    if (cudaMalloc(&h.w_dev, w_total) != cudaSuccess) return fail_free("out of memory (packed weights)");
     for (size_t c = 0; c < chunks.size(); ++c) {
       const WSrc& w = wsrc[c];
       pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, op.cout, w.tap, w.ci0, w.CK, p.N,
                                                 reinterpret_cast<__half*>(h.w_dev + chunks[c].w_off));
     }
-    cudaMemcpyAsync(h.chunks_dev, chunks.data(), sizeof(ChunkDesc) * chunks.size(), cudaMemcpyHostToDevice, stream);
-    cudaStreamSynchronize(stream);   // `chunks` is a host temporary
+    for (size_t c = 0; c < chunks.size(); ++c) p.chunks[c] = chunks[c];
     p.wchunks = h.w_dev;
-    p.chunks = h.chunks_dev;
     p.bias = net->blob + op.b;
     if (p.kind == TC_CONVBLOCK) {
       p.gamma = net->blob + op.gn_w;

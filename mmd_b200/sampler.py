@@ -21,6 +21,32 @@ from . import _lib
 from .diffusion import GaussianDiffusionModel, _run_step, lower_for_step
 
 
+def shard_robots(n_robots_total: int, world_size: int, rank: int):
+    """Contiguous robot block of `rank` (flatten (R, K), split contiguous robot blocks across GPUs)."""
+    per = (n_robots_total + world_size - 1) // world_size
+    lo = min(rank * per, n_robots_total)
+    return lo, min(lo + per, n_robots_total)
+
+
+def gather_peers(peers_local: torch.Tensor, n_robots_total: int, group=None) -> torch.Tensor:
+    """All-gather of the representative paths: [R_local, H, 2] per rank -> [R_total, H, 2] in robot order.  One
+    collective per guided timestep (16 KiB at R=32): latency-bound; NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = peers_local.shape[0]
+    if per * world == n_robots_total:
+        out = torch.empty(n_robots_total, *peers_local.shape[1:], dtype=peers_local.dtype, device=peers_local.device)
+        dist.all_gather_into_tensor(out, peers_local.contiguous(), group=group)
+        return out
+    # ragged last shard: pad to the common block size
+    blk = (n_robots_total + world - 1) // world
+    pad = torch.zeros(blk, *peers_local.shape[1:], dtype=peers_local.dtype, device=peers_local.device)
+    pad[:per] = peers_local
+    out = torch.empty(blk * world, *peers_local.shape[1:], dtype=peers_local.dtype, device=peers_local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:n_robots_total]
+
+
 class MultiRobotSampler:
     def __init__(self, model: GaussianDiffusionModel, guide, n_guide_steps=20, t_start_guide=None, noise_std=0.5,
                  n_diffusion_steps_without_noise=1, peer_radius=2.4 * 0.05, peer_weight=2e-2, rep_index=0,
@@ -88,7 +114,7 @@ class MultiRobotSampler:
                 _lib.check(lib.mmdk_publish_peers(C.byref(env), R, K, H, self.rep_index, _lib.ptr(x),
                                                   _lib.ptr(peers_local), _lib.stream_ptr()))
                 if distributed:
-                    torch.distributed.all_gather_into_tensor(peers, peers_local, group=self.pg)
+                    peers.copy_(gather_peers(peers_local, R_total, self.pg))
             t = max(i, 0)
             model.model.forward_t(x, t, precision=model.unet_precision, out=eps)
             sc = model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True)
