@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     }
   } else {
     // ================= epilogue: 8 warps; thread = (TMEM lane = image row, column half) =================
+    // The accumulators are streamed out of TMEM eight (or sixteen) columns at a time inside rolled loops: TMEM reads
+    // are cheap, while a fully unrolled 64-values-in-registers epilogue is ~200 KB of SASS and runs at I-cache-miss
+    // speed (ncu: 22% of stall samples "no_instructions" on the unrolled version).
     float* prm = reinterpret_cast<float*>(smem + p.smem_scratch_off);   // bias | gamma | beta | cond | res_bias, N each
     float2* part = reinterpret_cast<float2*>(prm + 5 * N);              // [NMT*128][8] (sum, M2) per row and group
     float* stat_mean = reinterpret_cast<float*>(part + NMT * 128 * 8);  // [ST][8]
@@ -315,160 +318,162 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       prm[3 * N + tid] = p.cond ? __ldg(p.cond + tid) : 0.f;
       prm[4 * N + tid] = p.res_bias ? __ldg(p.res_bias + tid) : 0.f;
     }
-    int rs[NMT], rp[NMT];
-    bool rvalid[NMT];
-#pragma unroll
-    for (int i = 0; i < NMT; ++i) {
-      const int q = 128 * i + row;
-      rs[i] = q / P;
-      rp[i] = q - rs[i] * P;
-      rvalid[i] = (rs[i] < ST) && (rp[i] < L) && (tile * ST + rs[i] < p.B);
-    }
     epi_bar();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs / residual reads only after the previous grid is complete
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
 
-    const int n_regions = (p.kind == TC_UP) ? 2 : 1;
-    for (int region = 0; region < n_regions; ++region) {
-      float v[NVH];
-      if (active) {
-#pragma unroll
+    if (p.kind == TC_CONVBLOCK) {
+      if constexpr (N >= 32) {
+        constexpr int CPG = N / 8;                 // channels per group
+        constexpr int GB = (CPG > 8) ? CPG : 8;    // columns per statistics block
+        // ---- GroupNorm statistics: per-row (sum, M2) -> one exchange -> Chan's combination (stable, 2 barriers)
+#pragma unroll 1
         for (int i = 0; i < NMT; ++i) {
-          if constexpr (NH >= 32) {
+          const int q = 128 * i + row;
+          const int si = q / P, pi = q - si * P;
+          const bool ok = (si < ST) && (pi < L) && (tile * ST + si < p.B);
+#pragma unroll 1
+          for (int gb = 0; gb < NH / GB; ++gb) {
+            float w[GB];
+            const int cb = c0 + gb * GB;
+            if constexpr (GB == 16) tmem_ld16(lane_base + i * N + cb, w); else tmem_ld8(lane_base + i * N + cb, w);
+            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < NH / 32; ++j)
-              tmem_ld32(lane_base + region * 128 + i * N + c0 + j * 32, v + i * NH + j * 32);
-          } else {
-            tmem_ld16(lane_base + region * 128 + i * N + c0, v + i * NH);
-          }
-        }
-        tmem_wait_ld();
+            for (int e = 0; e < GB; ++e) w[e] += prm[cb + e];
 #pragma unroll
-        for (int c = 0; c < NH; ++c) {
-          const float b = prm[c0 + c];
+            for (int g = 0; g < GB / CPG; ++g) {
+              float sm = 0.f;
 #pragma unroll
-          for (int i = 0; i < NMT; ++i) v[i * NH + c] += b;
-        }
-      }
-
-      if (p.kind == TC_CONVBLOCK) {
-        if constexpr (N >= 32) {
-          constexpr int CPG = N / 8;          // channels per group
-          constexpr int GH = NH / CPG;        // groups per thread (4)
-          // ---- GroupNorm statistics: per-row (sum, M2) -> one exchange -> Chan's combination (stable, 2 barriers)
-#pragma unroll
-          for (int i = 0; i < NMT; ++i)
-#pragma unroll
-            for (int g = 0; g < GH; ++g) {
-              float s = 0.f;
-#pragma unroll
-              for (int c = 0; c < CPG; ++c) s += v[i * NH + g * CPG + c];
-              const float m = s * (1.f / CPG);
+              for (int c = 0; c < CPG; ++c) sm += w[g * CPG + c];
+              const float m = sm * (1.f / CPG);
               float m2 = 0.f;
 #pragma unroll
-              for (int c = 0; c < CPG; ++c) { const float d = v[i * NH + g * CPG + c] - m; m2 = fmaf(d, d, m2); }
-              part[(i * 128 + row) * 8 + half * GH + g] = rvalid[i] ? make_float2(s, m2) : make_float2(0.f, 0.f);
-            }
-          epi_bar();
-          if (tid < ST * 8) {
-            const int s = tid >> 3, g = tid & 7;
-            const float inv_n = 1.f / (float)(CPG * L);
-            float sum = 0.f;
-            for (int pp = 0; pp < L; ++pp) sum += part[(s * P + pp) * 8 + g].x;
-            const float mean = sum * inv_n;
-            float m2 = 0.f;
-            for (int pp = 0; pp < L; ++pp) {
-              const float2 e = part[(s * P + pp) * 8 + g];
-              const float d = e.x * (1.f / CPG) - mean;
-              m2 += e.y + (float)CPG * d * d;
-            }
-            stat_mean[tid] = mean;
-            stat_rstd[tid] = rsqrtf(m2 * inv_n + 1e-5f);
-          }
-          epi_bar();
-          // ---- normalise, Mish, +cond, +residual, split, store ----
-#pragma unroll
-          for (int i = 0; i < NMT; ++i) {
-            const int r = 2 + 128 * i + row;
-            float r1[8];
-            // identity residual: issue the (L2-latency) loads of panel pc+1 before the arithmetic of panel pc
-            uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
-            const uint8_t* rbase = p.res_id ? p.res_id + (size_t)tile * p.res_id_tile_bytes + (size_t)r * 16 : nullptr;
-            const size_t rplane = (size_t)(p.res_id_C / 8) * p.res_id_rows * 16;
-            if (rbase && rvalid[i]) {
-              rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16));
-              rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16 + rplane));
-            }
-#pragma unroll
-            for (int pc = 0; pc < NH / 8; ++pc) {
-              const int pcg = c0 / 8 + pc;     // global panel index
-              const uint4 ch = rh, cl = rl;
-              if (rbase && rvalid[i] && pc + 1 < NH / 8) {
-                rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(pcg + 1) * p.res_id_rows * 16));
-                rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(pcg + 1) * p.res_id_rows * 16 + rplane));
-              }
-              if (p.res_bias != nullptr) {     // residual 1x1 conv lives in accumulator region 1
-                tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, r1);
-                tmem_wait_ld();
-              }
-              if (rvalid[i]) {
-                float y[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int cl = pc * 8 + e;            // column inside this thread's half
-                  const int c = c0 + cl;                // channel
-                  const int g = c / CPG;
-                  const float a = stat_rstd[rs[i] * 8 + g];
-                  float t = (v[i * NH + cl] - stat_mean[rs[i] * 8 + g]) * a;
-                  t = fmaf(t, prm[N + c], prm[2 * N + c]);
-                  t = mish_fast(t) + prm[3 * N + c];
-                  if (p.res_bias) t += r1[e] + prm[4 * N + c];
-                  y[e] = t;
-                }
-                if (rbase) add8(ch, cl, y);
-                uint4 hi, lo;
-                split8(y, hi, lo);
-                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)pcg * p.out_rows + r) * 16;
-                *reinterpret_cast<uint4*>(ob) = hi;
-                *reinterpret_cast<uint4*>(ob + (size_t)(p.out_C / 8) * p.out_rows * 16) = lo;
-              }
+              for (int c = 0; c < CPG; ++c) { const float d = w[g * CPG + c] - m; m2 = fmaf(d, d, m2); }
+              part[q * 8 + cb / CPG + g] = ok ? make_float2(sm, m2) : make_float2(0.f, 0.f);
             }
           }
         }
-      } else if (p.kind == TC_DOWN || p.kind == TC_UP) {
-        if constexpr (N >= 32) {
-          const int Po = p.out_L + 2;
+        epi_bar();
+        if (tid < ST * 8) {
+          const int sidx = tid >> 3, g = tid & 7;
+          const float inv_n = 1.f / (float)(CPG * L);
+          float sum = 0.f;
+          for (int pp = 0; pp < L; ++pp) sum += part[(sidx * P + pp) * 8 + g].x;
+          const float mean = sum * inv_n;
+          float m2 = 0.f;
+          for (int pp = 0; pp < L; ++pp) {
+            const float2 e = part[(sidx * P + pp) * 8 + g];
+            const float d = e.x * (1.f / CPG) - mean;
+            m2 += e.y + (float)CPG * d * d;
+          }
+          stat_mean[tid] = mean;
+          stat_rstd[tid] = rsqrtf(m2 * inv_n + 1e-5f);
+        }
+        epi_bar();
+        // ---- normalise, Mish, +cond, +residual, split, store ----
+        const size_t rplane = (size_t)(p.res_id_C / 8) * p.res_id_rows * 16;
+        const size_t oplane = (size_t)(p.out_C / 8) * p.out_rows * 16;
+#pragma unroll 1
+        for (int i = 0; i < NMT; ++i) {
+          const int q = 128 * i + row;
+          const int si = q / P, pi = q - si * P;
+          const bool ok = (si < ST) && (pi < L) && (tile * ST + si < p.B);
+          const int r = 2 + q;
+          // identity residual: issue the (L2-latency) loads of panel pc+1 before the arithmetic of panel pc
+          const uint8_t* rbase = (p.res_id && ok) ? p.res_id + (size_t)tile * p.res_id_tile_bytes + (size_t)r * 16 : nullptr;
+          uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
+          if (rbase) {
+            rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16));
+            rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16 + rplane));
+          }
+          uint8_t* obase = p.out + (size_t)tile * p.out_tile_bytes + (size_t)r * 16;
+#pragma unroll 1
+          for (int pc = 0; pc < NH / 8; ++pc) {
+            const int cb = c0 + pc * 8;          // first channel of this panel
+            const uint4 ch = rh, cl = rl;
+            if (rbase && pc + 1 < NH / 8) {
+              rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(cb / 8 + 1) * p.res_id_rows * 16));
+              rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(cb / 8 + 1) * p.res_id_rows * 16 + rplane));
+            }
+            float y[8], r1[8];
+            tmem_ld8(lane_base + i * N + cb, y);
+            if (p.res_bias != nullptr) tmem_ld8(lane_base + 128 + i * N + cb, r1);   // residual 1x1 conv: region 1
+            tmem_wait_ld();
+            if (ok) {
+              const int g = cb / CPG;            // CPG >= 4 and 8 | cb: a panel spans 8/CPG groups
 #pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = cb + e;
+                const int ge = (CPG >= 8) ? g : g + e / CPG;
+                float t = (y[e] + prm[c] - stat_mean[si * 8 + ge]) * stat_rstd[si * 8 + ge];
+                t = fmaf(t, prm[N + c], prm[2 * N + c]);
+                t = mish_fast(t) + prm[3 * N + c];
+                if (p.res_bias) t += r1[e] + prm[4 * N + c];
+                y[e] = t;
+              }
+              if (rbase) add8(ch, cl, y);
+              uint4 hi, lo;
+              split8(y, hi, lo);
+              uint8_t* ob = obase + (size_t)(cb / 8) * p.out_rows * 16;
+              *reinterpret_cast<uint4*>(ob) = hi;
+              *reinterpret_cast<uint4*>(ob + oplane) = lo;
+            }
+          }
+        }
+      }
+    } else if (p.kind == TC_DOWN || p.kind == TC_UP) {
+      if constexpr (N >= 32) {
+        const int Po = p.out_L + 2;
+        const size_t oplane = (size_t)(p.out_C / 8) * p.out_rows * 16;
+        const int n_regions = (p.kind == TC_UP) ? 2 : 1;
+#pragma unroll 1
+        for (int region = 0; region < n_regions; ++region) {
+#pragma unroll 1
           for (int i = 0; i < NMT; ++i) {
-            bool ok = rvalid[i];
+            const int q = 128 * i + row;
+            const int si = q / P, pi = q - si * P;
+            bool ok = (si < ST) && (pi < L) && (tile * ST + si < p.B);
             int ro;
             if (p.kind == TC_DOWN) {   // stride-2 conv evaluated at every position; keep the even ones
-              ok = ok && ((rp[i] & 1) == 0);
-              ro = 2 + rs[i] * Po + (rp[i] >> 1);
+              ok = ok && ((pi & 1) == 0);
+              ro = 2 + si * Po + (pi >> 1);
             } else {                    // transposed conv: region 0 -> output 2p, region 1 -> 2p + 1
-              ro = 2 + rs[i] * Po + 2 * rp[i] + region;
+              ro = 2 + si * Po + 2 * pi + region;
             }
-            if (ok) {
+            uint8_t* obase = p.out + (size_t)tile * p.out_tile_bytes + (size_t)ro * 16;
+#pragma unroll 1
+            for (int pc = 0; pc < NH / 8; ++pc) {
+              const int cb = c0 + pc * 8;
+              float y[8];
+              tmem_ld8(lane_base + region * 128 + i * N + cb, y);
+              tmem_wait_ld();
+              if (ok) {
 #pragma unroll
-              for (int pc = 0; pc < NH / 8; ++pc) {
+                for (int e = 0; e < 8; ++e) y[e] += prm[cb + e];
                 uint4 hi, lo;
-                split8(v + i * NH + pc * 8, hi, lo);
-                uint8_t* ob = p.out + (size_t)tile * p.out_tile_bytes + ((size_t)(c0 / 8 + pc) * p.out_rows + ro) * 16;
+                split8(y, hi, lo);
+                uint8_t* ob = obase + (size_t)(cb / 8) * p.out_rows * 16;
                 *reinterpret_cast<uint4*>(ob) = hi;
-                *reinterpret_cast<uint4*>(ob + (size_t)(p.out_C / 8) * p.out_rows * 16) = lo;
+                *reinterpret_cast<uint4*>(ob + oplane) = lo;
               }
             }
           }
         }
-      } else if (active) {  // TC_FINAL: eps [B][L][4]
-#pragma unroll
-        for (int i = 0; i < NMT; ++i) {
-          if (rvalid[i]) {
-            const size_t b = (size_t)tile * ST + rs[i];
-            *reinterpret_cast<float4*>(p.eps + (b * L + rp[i]) * 4) =
-                make_float4(v[i * NH + 0], v[i * NH + 1], v[i * NH + 2], v[i * NH + 3]);
-          }
+      }
+    } else if (active) {  // TC_FINAL: eps [B][L][4]
+#pragma unroll 1
+      for (int i = 0; i < NMT; ++i) {
+        const int q = 128 * i + row;
+        const int si = q / P, pi = q - si * P;
+        const bool ok = (si < ST) && (pi < L) && (tile * ST + si < p.B);
+        float y[8];
+        tmem_ld8(lane_base + i * N, y);
+        tmem_wait_ld();
+        if (ok) {
+          const size_t b = (size_t)tile * ST + si;
+          *reinterpret_cast<float4*>(p.eps + (b * L + pi) * 4) =
+              make_float4(y[0] + prm[0], y[1] + prm[1], y[2] + prm[2], y[3] + prm[3]);
         }
       }
     }
