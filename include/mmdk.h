@@ -84,6 +84,10 @@ int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond,
 int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int* c_out, int* l_out, int* n_ops_out,
                         void* stream);
 
+/* Debug: from the next MMDK_UNET_F16X3 forward on, op `op_index` writes a per-CTA clock64 timeline into
+ * dbg_dev [n_tiles, 16] int64 (slot 15 = SM id); op_index = -1 / dbg_dev = NULL switches it off. */
+int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Guide + DDPM step  (mmd/models/diffusion_models/guides.py:152-253, sample_functions.py:41-107,
  * diffusion_model_base.py:126-160, MPB/planners/costs/cost_functions.py, TR/environments/grid_map_sdf.py)

@@ -50,7 +50,7 @@ class StepScalars(C.Structure):
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
-    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_cross_condition",
+    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize",
 ]
 
@@ -80,6 +80,7 @@ def load():
     lib.mmdk_unet_forward.argtypes = [vp, i, vp, i, i, vp, vp]
     lib.mmdk_unet_cond_row.argtypes = [vp, i, vp, c_int_p, vp]
     lib.mmdk_unet_debug_tap.argtypes = [vp, i, vp, c_int_p, c_int_p, c_int_p, vp]
+    lib.mmdk_unet_debug_timeline.argtypes = [vp, i, vp, vp]
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]

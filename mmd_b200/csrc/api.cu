@@ -91,4 +91,9 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
   return unet_tc_tap(net->impl, op_index, out_dev, c_out, l_out, (cudaStream_t)stream);
 }
 
+int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream) {
+  if (!net) return fail(MMDK_EINVAL, "null argument");
+  return unet_tc_timeline(net->impl, op_index, dbg_dev, (cudaStream_t)stream);
+}
+
 }  // extern "C"

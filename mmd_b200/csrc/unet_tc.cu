@@ -34,6 +34,9 @@ constexpr int TC_THREADS = 320;
 constexpr int TMEM_COLS = 256;
 constexpr int MAX_SRC = 4;
 constexpr int MAX_CHUNKS = 48;
+constexpr int TC_CLUSTER = 1;    // >1: CTAs per cluster sharing every weight chunk through TMA multicast.  Measured on B200 (r01): the main
+                                 // loop is tensor-pipe bound (two resident CTAs share the pipe), not L2 bound, and 4-CTA clusters cost
+                                 // scheduling tails (1.85 vs 1.29 ms per forward) -> off by default, code path kept.
 
 struct ChunkDesc {
   uint32_t a_off;    // smem byte offset of the chunk's first A panel (plane hi, buffer row 0)
@@ -72,6 +75,8 @@ struct TcOpParams {
   int out_L, out_rows, out_C;
   float* eps;
   uint32_t smem_w_off, smem_scratch_off, smem_bar_off;
+  int cluster;      // CTAs per cluster sharing every weight chunk through TMA multicast (1 = off)
+  long long* dbg;   // optional per-CTA timeline [n_tiles][16] (clock64), nullptr in production
   ChunkDesc chunks[MAX_CHUNKS];   // in the kernel parameter (constant) bank: no dependent global loads per chunk
 };
 
@@ -107,6 +112,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -205,6 +227,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   constexpr int NVH = NMT * NH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
+  const int CS = p.cluster;
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+  const int tile_ld = tile < p.n_tiles ? tile : p.n_tiles - 1;   // padding CTAs of the last cluster read a valid image
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_base + p.smem_bar_off;
   // barriers: [0] in_full, [1..3] w_full, [4..6] w_empty, [7] acc_full ; then the TMEM base pointer
@@ -215,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 
   if (tid == 0) {
     mbar_init(bar_in, 1);
-    for (int s = 0; s < MAX_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+    for (int s = 0; s < MAX_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, (uint32_t)CS); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -225,9 +251,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // barrier inits visible to the peers before any multicast copy / remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+#define MMDK_STAMP(k) do { if (p.dbg && tile < p.n_tiles) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
+  if (tid == 0) { MMDK_STAMP(0); if (p.dbg && tile < p.n_tiles) { unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); p.dbg[(size_t)tile * 16 + 15] = smid; } }
 
   // programmatic dependent launch: everything above (and the weight prefetch below) overlaps the previous layer's
   // tail; activations written by earlier kernels are only touched after griddepcontrol.wait
@@ -240,15 +269,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       for (; c_pre < p.n_chunks && c_pre < WS; ++c_pre) {
         const ChunkDesc cd = p.chunks[c_pre];
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
-        bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        if (CS > 1) {
+          const uint32_t part = cd.w_bytes / (uint32_t)CS, po = crank * part;
+          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, p.wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
+        } else {
+          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        }
         if (++st == WS) { st = 0; ph ^= 1; }
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      MMDK_STAMP(1);
       uint32_t total = 0;
       for (int s = 0; s < p.n_src; ++s) total += p.src_tile_bytes[s];
       mbar_expect_tx(bar_in, total);
       for (int s = 0; s < p.n_src; ++s) {
-        const uint8_t* g = p.src[s] + (size_t)tile * p.src_tile_bytes[s];
+        const uint8_t* g = p.src[s] + (size_t)tile_ld * p.src_tile_bytes[s];
         uint32_t off = 0;
         while (off < p.src_tile_bytes[s]) {
           uint32_t n = min(p.src_tile_bytes[s] - off, 32768u);
@@ -260,9 +295,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         mbar_wait(bar_wempty + 8 * st, ph ^ 1);
         const ChunkDesc cd = p.chunks[c];
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
-        bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        if (CS > 1) {
+          const uint32_t part = cd.w_bytes / (uint32_t)CS, po = crank * part;
+          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, p.wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
+        } else {
+          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+        }
         if (++st == WS) { st = 0; ph ^= 1; }
       }
+      MMDK_STAMP(2);
     }
   } else if (warp == 8) {
     // ================= MMA issuer (one thread) =================
@@ -270,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       // instruction descriptor: D fp32 (bit 4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_in, 0);
+      MMDK_STAMP(3);
       int st = 0, ph = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         const ChunkDesc cd = p.chunks[c];
@@ -290,18 +332,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
           }
         }
-        tc_commit(bar_wempty + 8 * st);   // frees the weight stage once these MMAs have read it
+        if (CS > 1) tc_commit_mc(bar_wempty + 8 * st, cmask);   // every CTA of the cluster must be done with the stage
+        else tc_commit(bar_wempty + 8 * st);                       // frees the weight stage once these MMAs have read it
         if (++st == WS) { st = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);
+      MMDK_STAMP(4);
     }
   } else {
     // ================= epilogue: 8 warps; thread = (TMEM lane = image row, column half) =================
     // The accumulators are streamed out of TMEM eight (or sixteen) columns at a time inside rolled loops: TMEM reads
     // are cheap, while a fully unrolled 64-values-in-registers epilogue is ~200 KB of SASS and runs at I-cache-miss
     // speed (ncu: 22% of stall samples "no_instructions" on the unrolled version).
-    float* prm = reinterpret_cast<float*>(smem + p.smem_scratch_off);   // bias | gamma | beta | cond | res_bias, N each
-    float2* part = reinterpret_cast<float2*>(prm + 5 * N);              // [NMT*128][8] (sum, M2) per row and group
+    float4* prm4 = reinterpret_cast<float4*>(smem + p.smem_scratch_off);   // per channel (bias, gamma, beta, cond)
+    float* prm_rb = reinterpret_cast<float*>(prm4 + N);                    // residual-conv bias
+    float2* part = reinterpret_cast<float2*>(prm_rb + N);               // [NMT*128][8] (sum, M2) per row and group
     float* stat_mean = reinterpret_cast<float*>(part + NMT * 128 * 8);  // [ST][8]
     float* stat_rstd = stat_mean + ST * 8;
     const int P = p.P, L = p.L;
@@ -312,16 +357,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     // stage the per-channel parameters while the MMAs run
     if (tid < N) {
-      prm[tid] = (tid < p.cout) ? __ldg(p.bias + tid) : 0.f;
-      prm[N + tid] = p.gamma ? __ldg(p.gamma + tid) : 1.f;
-      prm[2 * N + tid] = p.beta ? __ldg(p.beta + tid) : 0.f;
-      prm[3 * N + tid] = p.cond ? __ldg(p.cond + tid) : 0.f;
-      prm[4 * N + tid] = p.res_bias ? __ldg(p.res_bias + tid) : 0.f;
+      prm4[tid] = make_float4((tid < p.cout) ? __ldg(p.bias + tid) : 0.f, p.gamma ? __ldg(p.gamma + tid) : 1.f,
+                              p.beta ? __ldg(p.beta + tid) : 0.f, p.cond ? __ldg(p.cond + tid) : 0.f);
+      prm_rb[tid] = p.res_bias ? __ldg(p.res_bias + tid) : 0.f;
     }
     epi_bar();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs / residual reads only after the previous grid is complete
+    if (tid == 0) MMDK_STAMP(5);
     mbar_wait_sleep(bar_acc, 0);
     tc_fence_after();
+    if (tid == 0) MMDK_STAMP(6);
 
     if (p.kind == TC_CONVBLOCK) {
       if constexpr (N >= 32) {
@@ -340,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             if constexpr (GB == 16) tmem_ld16(lane_base + i * N + cb, w); else tmem_ld8(lane_base + i * N + cb, w);
             tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < GB; ++e) w[e] += prm[cb + e];
+            for (int e = 0; e < GB; ++e) w[e] += prm4[cb + e].x;
 #pragma unroll
             for (int g = 0; g < GB / CPG; ++g) {
               float sm = 0.f;
@@ -354,7 +399,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             }
           }
         }
+        if (tid == 0) MMDK_STAMP(7);
         epi_bar();
+        if (tid == 0) MMDK_STAMP(8);
         if (tid < ST * 8) {
           const int sidx = tid >> 3, g = tid & 7;
           const float inv_n = 1.f / (float)(CPG * L);
@@ -371,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           stat_rstd[tid] = rsqrtf(m2 * inv_n + 1e-5f);
         }
         epi_bar();
+        if (tid == 0) MMDK_STAMP(9);
         // ---- normalise, Mish, +cond, +residual, split, store ----
         const size_t rplane = (size_t)(p.res_id_C / 8) * p.res_id_rows * 16;
         const size_t oplane = (size_t)(p.out_C / 8) * p.out_rows * 16;
@@ -406,10 +454,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
               for (int e = 0; e < 8; ++e) {
                 const int c = cb + e;
                 const int ge = (CPG >= 8) ? g : g + e / CPG;
-                float t = (y[e] + prm[c] - stat_mean[si * 8 + ge]) * stat_rstd[si * 8 + ge];
-                t = fmaf(t, prm[N + c], prm[2 * N + c]);
-                t = mish_fast(t) + prm[3 * N + c];
-                if (p.res_bias) t += r1[e] + prm[4 * N + c];
+                const float4 pr = prm4[c];
+                float t = (y[e] + pr.x - stat_mean[si * 8 + ge]) * stat_rstd[si * 8 + ge];
+                t = fmaf(t, pr.y, pr.z);
+                t = mish_fast(t) + pr.w;
+                if (p.res_bias) t += r1[e] + prm_rb[c];
                 y[e] = t;
               }
               if (rbase) add8(ch, cl, y);
@@ -450,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
               tmem_wait_ld();
               if (ok) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] += prm[cb + e];
+                for (int e = 0; e < 8; ++e) y[e] += prm4[cb + e].x;
                 uint4 hi, lo;
                 split8(y, hi, lo);
                 uint8_t* ob = obase + (size_t)(cb / 8) * p.out_rows * 16;
@@ -473,13 +522,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         if (ok) {
           const size_t b = (size_t)tile * ST + si;
           *reinterpret_cast<float4*>(p.eps + (b * L + pi) * 4) =
-              make_float4(y[0] + prm[0], y[1] + prm[1], y[2] + prm[2], y[3] + prm[3]);
+              make_float4(y[0] + prm4[0].x, y[1] + prm4[1].x, y[2] + prm4[2].x, y[3] + prm4[3].x);
         }
       }
     }
   }
+  if (tid == 0) MMDK_STAMP(10);
   tc_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / arrive on this CTA's smem
+  else __syncthreads();
+  if (tid == 0) MMDK_STAMP(11);
   if (warp == 8) {
     __syncwarp();
     tc_fence_after();
@@ -582,15 +634,24 @@ static int launch_tc(const TcOpHost& o, cudaStream_t stream) {
     configured = 232448;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)o.prm.n_tiles);
+  const int cs = o.prm.cluster;
+  cfg.gridDim = dim3((unsigned)(((o.prm.n_tiles + cs - 1) / cs) * cs));
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = o.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  int na = 1;
+  if (cs > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cs;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    na = 2;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NV, N>, o.prm), "conv_tc_kernel launch");
 }
 
@@ -730,6 +791,7 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
                                                 reinterpret_cast<__half*>(h.w_dev + chunks[c].w_off));
     }
     for (size_t c = 0; c < chunks.size(); ++c) p.chunks[c] = chunks[c];
+    p.cluster = TC_CLUSTER;
     p.wchunks = h.w_dev;
     p.bias = net->blob + op.b;
     if (p.kind == TC_CONVBLOCK) {
@@ -775,6 +837,14 @@ int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float
     else rc = launch_tc<64, 16>(h, stream);
     if (rc != MMDK_OK) return rc;
   }
+  return MMDK_OK;
+}
+
+int unet_tc_timeline(UnetImpl* net, int op_index, long long* dbg_dev, cudaStream_t stream) {
+  if (!net->tc) return fail(MMDK_EINVAL, "run a tensor-core forward first");
+  TcState* st = net->tc;
+  if (op_index >= (int)st->ops.size()) return fail(MMDK_EINVAL, "op index out of range");
+  for (size_t j = 0; j < st->ops.size(); ++j) st->ops[j].prm.dbg = ((int)j == op_index) ? dbg_dev : nullptr;
   return MMDK_OK;
 }
 
