@@ -12,4 +12,5 @@ from .costs import CostCollision, CostComposite, CostConstraint, CostGPTrajector
 from .tasks import PlanningTask, RobotPlanarDisk  # noqa: F401
 from .datasets import LimitsNormalizer, TrajectoryDataset  # noqa: F401
 from .sampler import MultiRobotSampler  # noqa: F401
+from .planners import MPD, DiffusionsEnsemble, MultiPointConstraint, PlannerOutput  # noqa: F401
 from . import envs  # noqa: F401

@@ -345,3 +345,76 @@ def test_classify_trajs_matches_oracle(pair, dev):
     ref_cost = port.compute_path_length(trajs) + port.compute_smoothness(trajs)
     assert rel_err(cost, ref_cost) < 1e-5
     assert 0 < free_idx.numel() < K
+
+
+def test_mpd_planner_call_surface(dev):
+    """MPD.__call__(start, goal, constraints_l) (mpd.py:306-405): chain equals the oracle's run_inference on the same
+    noise (GP term off for the free-running comparison), PlannerOutput fields are populated, best index is a free
+    trajectory with minimal path length + smoothness."""
+    import mmd_b200 as M
+    T, K = 25, 16
+    o = build_oracle("EnvConveyor2D", T=T, w_smooth=0.0)
+    unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    unet.load_state_dict(o["P"], strict=True)
+    model = M.GaussianDiffusionModel(model=unet, variance_schedule="exponential", n_diffusion_steps=T, predict_epsilon=True)
+    start, goal = torch.tensor([-0.8, -0.6]), torch.tensor([0.8, 0.6])
+    planner = M.MPD("EnvConveyor2D-RobotPlanarDisk", "mmd", start, goal, n_samples=K, model=model, device="cuda:0",
+                    weight_grad_cost_smoothness=0.0, seed=18)
+    qs, rng, rad = random_constraints(40, seed=5)
+    cons = [M.MultiPointConstraint([q.to(dev) for q in qs], rng.tolist(), rad.tolist(), is_soft=True)]
+    noise = torch.randn(T + 2, K, 64, 4, generator=torch.Generator().manual_seed(3))
+    hc = port.hard_conds_from_start_goal(start, goal, o["norm"])
+    o["guide"].extra = [port.Constraint(qs, rng, rad, True)]
+    ref = port.run_inference(o["model"], hc, K, noise, guide=o["guide"])
+    o["guide"].extra = []
+    cc = [M.CostConstraint(planner.robot, 64, q_l=c.get_q_l(), traj_range_l=c.get_t_range_l(), radius_l=c.radius_l,
+                           is_soft=True, tensor_args=planner.tensor_args) for c in cons]
+    chain = planner.run_constrained_inference(cc, noise=noise.to(dev))
+    e = _per_traj(chain[-1], ref[-1])
+    print(f"MPD chain vs oracle: median={float(e.median()):.2e} max={float(e.max()):.2e}")
+    assert float(e.median()) < 1e-4 and float(e.quantile(0.9)) < 1e-3
+    out = planner(start.to(dev), goal.to(dev), constraints_l=cons)
+    assert out.trajs_iters.shape == (T + 2, K, 64, 4) and out.trajs_final.shape == (K, 64, 4)
+    n_free = 0 if out.trajs_final_free is None else out.trajs_final_free.shape[0]
+    n_coll = 0 if out.trajs_final_coll is None else out.trajs_final_coll.shape[0]
+    assert n_free + n_coll == K
+    if n_free:
+        free_idx, _ = port.get_trajs_free_idxs(out.trajs_iters[-1].cpu(), o["guide"].grid)
+        assert torch.equal(out.trajs_final_free_idxs.reshape(-1).cpu(), free_idx)
+        assert int(out.idx_best_traj) in free_idx.tolist()
+    with pytest.raises(ValueError):
+        planner(goal.to(dev), start.to(dev))
+
+
+def test_diffusions_ensemble_two_tiles(dev):
+    """DiffusionsEnsemble.run_inference (diffusion_ensemble.py:56-106,224-268): two tiles stitched by cross conditioning
+    (63 -> 0 through the (2, 0) tile transform).  Final frames vs the oracle (chain frames of later tiles alias in the
+    reference, oracle/port.py ensemble_p_sample_loop)."""
+    import mmd_b200 as M
+    T, K = 25, 6
+    o = build_oracle("EnvEmptyNoWait2D", T=T, w_smooth=0.0)
+    p0 = build_product(dev, "EnvEmptyNoWait2D", T=T, P=o["P"], w_smooth=0.0)
+    p1 = build_product(dev, "EnvEmptyNoWait2D", T=T, P=o["P"], w_smooth=0.0)
+    transforms = {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}
+    norm = o["norm"]
+    s0 = norm.normalize(torch.tensor([-0.7, 0.1, 0.0, 0.0]))
+    g1 = norm.normalize(torch.tensor([0.6, -0.2, 0.0, 0.0]))
+    hard = {0: {0: s0}, 1: {63: g1}}
+    cross = {(0, 1): (-1, 0)}
+    g = torch.Generator().manual_seed(21)
+    noise = {m: torch.randn(T + 2, K, 64, 4, generator=g) for m in (0, 1)}
+    guides = {m: port.GuideSpec(o["guide"].grid, norm, w_smooth=0.0) for m in (0, 1)}
+    kw = {m: dict(guide=guides[m], n_guide_steps=20, t_start_guide=13, noise_std=0.5) for m in (0, 1)}
+    ref = port.ensemble_p_sample_loop({0: o["model"], 1: o["model"]},
+                                      {m: port.repeat_hard_conds(h, K) for m, h in hard.items()}, cross, transforms,
+                                      noise, T, 1, kw)
+    ens = M.DiffusionsEnsemble({0: p0["model"], 1: p1["model"]}, {m: t.to(dev) for m, t in transforms.items()})
+    skw = [dict(guide=p0["guide"], n_guide_steps=20, t_start_guide=13, noise_std_extra_schedule_fn=lambda x: 0.5),
+           dict(guide=p1["guide"], n_guide_steps=20, t_start_guide=13, noise_std_extra_schedule_fn=lambda x: 0.5)]
+    out = ens.run_inference(None, {m: {k: v.to(dev) for k, v in h.items()} for m, h in hard.items()}, cross,
+                            n_samples=K, return_chain=False, sample_kwargs=skw, n_diffusion_steps_without_noise=1,
+                            noise={m: n.to(dev) for m, n in noise.items()})
+    for m in (0, 1):
+        e = _per_traj(out[m], ref[m][-1])
+        print(f"ensemble tile {m}: median={float(e.median()):.2e} max={float(e.max()):.2e}")
+        assert float(e.median()) < 1e-4 and float(e.max()) < 2e-2
