@@ -35,6 +35,7 @@ struct StepArgs {
   float* grad_out;  // taps mode
   float* raw_out;
   int n_costs_max;
+  int peers_in_smem;  // the [n_peers, H, 2] table is staged in shared memory once per launch (it is constant during it)
 };
 
 __device__ __forceinline__ void clip_by_norm(float g[4], float max_norm) {
@@ -110,6 +111,13 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
   if (a.cpg > 1) cg::this_cluster().sync();  // flags zeroed everywhere before any remote write
   else __syncthreads();
 
+  // lock-step peers: constant for the whole launch -> one coalesced copy into shared memory, 20 x reuse
+  float2* s_peers = reinterpret_cast<float2*>(s_xu + (size_t)a.spc * H);
+  if (a.grp.peers_dev && a.peers_in_smem) {
+    const float2* gp = reinterpret_cast<const float2*>(a.grp.peers_dev);
+    for (int i = tid; i < a.grp.n_peers * H; i += blockDim.x) s_peers[i] = __ldg(gp + i);
+    __syncthreads();
+  }
   const int n_iter = TAPS ? 1 : a.sc.n_guide_steps;
   int o_beg = 0, o_end = 0;
   if (a.grp.obj_ptr_dev) { o_beg = a.grp.obj_ptr_dev[g]; o_end = a.grp.obj_ptr_dev[g + 1]; }
@@ -236,9 +244,11 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
       float gk[4] = {0.f, 0.f, 0.f, 0.f};
       const float r = a.grp.peer_radius;
       const float r2_far = r * r * 1.0001f;
-      for (int j = 0; j < a.grp.n_peers; ++j) {
+      const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev)) + h;
+#pragma unroll 4
+      for (int j = 0; j < a.grp.n_peers; ++j, pq += H) {
         if (j == self_peer) continue;
-        float2 q = __ldg(reinterpret_cast<const float2*>(a.grp.peers_dev) + (size_t)j * H + h);
+        const float2 q = *pq;
         float dx = xu[0] - q.x, dy = xu[1] - q.y;
         float d2 = dx * dx + dy * dy;
         if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
@@ -284,7 +294,8 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
 
 static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
   const int threads = args.H * args.spc;
-  const size_t smem = sizeof(float4) * (size_t)args.H * args.spc;
+  size_t smem = sizeof(float4) * (size_t)args.H * args.spc;
+  if (args.peers_in_smem) smem += sizeof(float2) * (size_t)args.grp.n_peers * args.H;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(args.grp.n_groups * args.cpg));
   cfg.blockDim = dim3((unsigned)threads);
@@ -325,6 +336,8 @@ static int plan_step(StepArgs& a) {
   spc = (K + cpg - 1) / cpg;
   a.spc = spc;
   a.cpg = cpg;
+  a.peers_in_smem = (a.grp.peers_dev != nullptr &&
+                     sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 48 * 1024) ? 1 : 0;
   return MMDK_OK;
 }
 
