@@ -312,6 +312,12 @@ static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  static bool big_smem_set = false;
+  if (smem > 48 * 1024 && !big_smem_set) {
+    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16384));
+    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16384));
+    big_smem_set = true;
+  }
   static bool np_set = false;
   if (args.cpg > 8 && !np_set) {
     MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -337,7 +343,7 @@ static int plan_step(StepArgs& a) {
   a.spc = spc;
   a.cpg = cpg;
   a.peers_in_smem = (a.grp.peers_dev != nullptr &&
-                     sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 48 * 1024) ? 1 : 0;
+                     sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 200 * 1024) ? 1 : 0;
   return MMDK_OK;
 }
 

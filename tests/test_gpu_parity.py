@@ -300,13 +300,19 @@ def test_peer_term_equals_constraint_object(pair, dev):
     reps = torch.stack([o["norm"].unnormalize(x[r * K:(r + 1) * K].clone())[0, :, :2] for r in range(R)])
     assert torch.equal(peers.cpu(), reps)
     peer_self = torch.arange(R, dtype=torch.int32, device=dev)
+    # a fleet larger than this rank's groups (other GPUs' robots): 200 rows = 102 KB > 48 KB exercises the opt-in
+    # large shared-memory staging of the table
+    extra = torch.rand(195, 64, 2, generator=g) * 1.6 - 0.8
+    reps = torch.cat((reps, extra), 0)
+    peers = reps.to(dev).contiguous()
+    n_all = reps.shape[0]
     env, grp, keep = lower_for_step(p["guide"], R, K, 64, dev, [None] * R, None, peers, peer_self, 0.12, 2e-2)
     grad = torch.empty_like(xd)
     _lib.check(_lib.lib().mmdk_guide_grad(C.byref(env), C.byref(grp), 64, _lib.ptr(xd), _lib.ptr(grad), None, 0,
                                           _lib.stream_ptr()))
-    hh = torch.arange(64, dtype=torch.float32).repeat(R - 1)
+    hh = torch.arange(64, dtype=torch.float32).repeat(n_all - 1)
     for r in range(R):
-        qs = torch.cat([reps[j] for j in range(R) if j != r], 0)
+        qs = torch.cat([reps[j] for j in range(n_all) if j != r], 0)
         o["guide"].extra = [port.Constraint(qs, torch.stack((hh, hh + 1), -1), torch.full((qs.shape[0],), 0.12), True, 2e-2)]
         ref = o["guide"](x[r * K:(r + 1) * K])
         o["guide"].extra = []
