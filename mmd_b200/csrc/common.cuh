@@ -27,6 +27,7 @@ enum OpType : int {
   OP_DOWN = 1,       // Conv1d(k3,s2,p1)                                               (layers.py:261-267)
   OP_UP = 2,         // ConvTranspose1d(k4,s2,p1)                                      (layers.py:270-276)
   OP_FINAL = 3,      // Conv1d(k1) -> eps [B,H,D]                                      (temporal_unet.py:116-119)
+  OP_ATTN = 4,       // Residual(PreNorm(LinearAttention)), in place                    (layers.py:177-229)
 };
 
 struct Op {

@@ -255,6 +255,76 @@ unet_ffma_kernel(const Op* __restrict__ ops, int n_ops, const float* __restrict_
         for (int s = 0; s < S; ++s) dst[s * sstride + co * pout + 2 + j] = acc[s];
       }
       zero_halo<S>(dst, op.cout, op.lout, sstride);
+    } else if (op.type == OP_ATTN) {
+      // Residual(PreNorm(LinearAttention)) (layers.py:177-229), heads=4, dim_head=32, one sample at a time:
+      // LayerNorm over channels -> qkv = W x (1x1, no bias) -> q *= 32^-1/2, k = softmax over positions ->
+      // context[h] = k[h] v[h]^T (32x32) -> out[h] = context[h]^T q[h] -> W_out out + b + x
+      const int C = op.cin, L = op.lin, pitch = L + 4;
+      float* scr = smem + S * sstride;          // qkv [384][L] | context [4][32][32] | mean [L] | rstd [L]
+      float* ctx = scr + 384 * L;
+      float* mu = ctx + 4 * 32 * 32;
+      float* rs = mu + L;
+      for (int s = 0; s < S; ++s) {
+        float* xs = smem + s * sstride + op.src + 2;
+        for (int n = threadIdx.x; n < L; n += blockDim.x) {
+          float m = 0.f;
+          for (int c = 0; c < C; ++c) m += xs[c * pitch + n];
+          m /= (float)C;
+          float v = 0.f;
+          for (int c = 0; c < C; ++c) { float d = xs[c * pitch + n] - m; v = fmaf(d, d, v); }
+          mu[n] = m;
+          rs[n] = 1.f / sqrtf(v / (float)C + 1e-5f);
+        }
+        __syncthreads();
+        for (int u = threadIdx.x; u < 384 * L; u += blockDim.x) {
+          const int o = u % 384, n = u / 384;
+          float acc = 0.f;
+          for (int c = 0; c < C; ++c) {
+            const float xn = (xs[c * pitch + n] - mu[n]) * rs[n] * __ldg(W + op.gn_w + c) + __ldg(W + op.gn_b + c);
+            acc = fmaf(__ldg(W + op.w + c * 384 + o), xn, acc);
+          }
+          scr[o * L + n] = (o < 128) ? acc * 0.17677669529663687f : acc;   // q * dim_head^-0.5
+        }
+        __syncthreads();
+        {  // softmax over positions of every k row (rows 128..255)
+          const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+          for (int r = warp; r < 128; r += nw) {
+            float* kr = scr + (128 + r) * L;
+            float mx = -INFINITY;
+            for (int n = lane; n < L; n += 32) mx = fmaxf(mx, kr[n]);
+            for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+            float sum = 0.f;
+            for (int n = lane; n < L; n += 32) { float e = expf(kr[n] - mx); kr[n] = e; sum += e; }
+            for (int o2 = 16; o2 > 0; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
+            const float inv = 1.f / sum;
+            for (int n = lane; n < L; n += 32) kr[n] *= inv;
+          }
+        }
+        __syncthreads();
+        for (int u = threadIdx.x; u < 4 * 32 * 32; u += blockDim.x) {   // context[h][d][e] = sum_n k[h][d][n] v[h][e][n]
+          const int e = u & 31, d = (u >> 5) & 31, h = u >> 10;
+          const float* kr = scr + (128 + h * 32 + d) * L;
+          const float* vr = scr + (256 + h * 32 + e) * L;
+          float acc = 0.f;
+          for (int n = 0; n < L; ++n) acc = fmaf(kr[n], vr[n], acc);
+          ctx[u] = acc;
+        }
+        __syncthreads();
+        for (int u = threadIdx.x; u < 128 * L; u += blockDim.x) {       // out[h][e][n] -> stored over the k rows
+          const int n = u % L, e = (u / L) & 31, h = u / (L * 32);
+          float acc = 0.f;
+          for (int d = 0; d < 32; ++d) acc = fmaf(ctx[(h * 32 + d) * 32 + e], scr[(h * 32 + d) * L + n], acc);
+          scr[(128 + h * 32 + e) * L + n] = acc;
+        }
+        __syncthreads();
+        for (int u = threadIdx.x; u < C * L; u += blockDim.x) {          // to_out (1x1) + bias + residual, in place
+          const int c = u % C, n = u / C;
+          float acc = __ldg(W + op.b + c);
+          for (int j = 0; j < 128; ++j) acc = fmaf(__ldg(W + op.res_w + j * C + c), scr[(128 + j) * L + n], acc);
+          xs[c * pitch + n] += acc;
+        }
+        __syncthreads();
+      }
     } else {  // OP_FINAL: 1x1 conv to state_dim channels, written straight to eps [B][H][D]
       const int pin = op.lin + 4;
       for (int u = threadIdx.x; u < S * op.lin * op.cout; u += blockDim.x) {
@@ -394,6 +464,22 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
                      cin != cout ? pre + ".residual_conv" : "");
   };
 
+  // Residual(PreNorm(LinearAttention(dim))) in place on `buf` (keys: <pre>.fn.norm.{g,b}, <pre>.fn.fn.to_qkv.weight,
+  // <pre>.fn.fn.to_out.{weight,bias})
+  auto attn = [&](const std::string& pre, int C, int len, int buf) -> bool {
+    Op o{};
+    o.type = OP_ATTN; o.cin = C; o.cout = C; o.lin = len; o.lout = len; o.src = buf; o.dst = buf;
+    o.w = bld.conv(pre + ".fn.fn.to_qkv.weight", C, 384, 1, false);        // [C][384]
+    o.res_w = bld.conv(pre + ".fn.fn.to_out.weight", 128, C, 1, false);    // [128][C]
+    o.b = bld.vec(pre + ".fn.fn.to_out.bias", C);
+    o.gn_w = bld.vec(pre + ".fn.norm.g", C);
+    o.gn_b = bld.vec(pre + ".fn.norm.b", C);
+    o.res_src = -1; o.cond = -1; o.res_b = -1;
+    wire(o, len + 4);
+    prod[buf] = (int)ops.size();
+    ops.push_back(o);
+    return bld.err.empty();
+  };
   int cur = R[0];  // input lives in R[0]
   int ri = 0;      // index of rotating buffer holding `cur` (when cur is a rotating buffer)
   auto other = [&](int a, int b) { for (int k = 0; k < 3; ++k) if (R[k] != a && R[k] != b) return R[k]; return -1; };
@@ -408,7 +494,7 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
     int o2 = (i >= 1) ? cat[i] + dims[i + 1] * (L[i] + 4) : other(cur, t2);  // skip goes to the upper half of CAT[i]
     if (!rtb(p + ".1", dims[i + 1], dims[i + 1], L[i], cur, t2, o2)) return MMDK_EINVAL;
     cur = o2;
-    if (cfg.self_attention) { bld.err = "self_attention executor not available in this build"; return MMDK_EINVAL; }
+    if (cfg.self_attention && !attn("downs." + std::to_string(i) + ".2", dims[i + 1], L[i], cur)) return MMDK_EINVAL;
     if (i < n - 1) {
       Op o{};
       o.type = OP_DOWN; o.cin = dims[i + 1]; o.cout = dims[i + 1]; o.lin = L[i]; o.lout = L[i + 1];
@@ -428,6 +514,7 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
     int t1 = other(cur, -1), o1 = other(cur, t1);
     if (!rtb("mid_block1", C, C, len, cur, t1, o1)) return MMDK_EINVAL;
     cur = o1;
+    if (cfg.self_attention && !attn("mid_attn", C, len, cur)) return MMDK_EINVAL;
     int t2 = other(cur, -1);
     int o2 = (n >= 2) ? cat[n - 1] : other(cur, t2);  // lower half of CAT[n-1]
     if (!rtb("mid_block2", C, C, len, cur, t2, o2)) return MMDK_EINVAL;
@@ -445,6 +532,7 @@ static int lower(Builder& bld, const mmdk_unet_config& cfg, std::vector<Op>& ops
     int t2 = other(cur, -1), o2 = other(cur, t2);
     if (!rtb(p + ".1", cmid, cmid, L[lvl], cur, t2, o2)) return MMDK_EINVAL;
     cur = o2;
+    if (cfg.self_attention && !attn(p + ".2", cmid, L[lvl], cur)) return MMDK_EINVAL;
     Op o{};
     o.type = OP_UP; o.cin = cmid; o.cout = cmid; o.lin = L[lvl]; o.lout = L[lvl - 1];
     o.src = cur;
@@ -546,7 +634,8 @@ int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* n
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int S = (int)((size_t)max_smem / (sizeof(float) * net->per_sample_floats));
+  net->attn_scratch_floats = cfg->self_attention ? (384 * cfg->horizon + 4 * 32 * 32 + 2 * cfg->horizon) : 0;
+  int S = (int)(((size_t)max_smem - sizeof(float) * net->attn_scratch_floats) / (sizeof(float) * net->per_sample_floats));
   if (S < 1) { unet_destroy(net); return fail(MMDK_EINVAL, "network activations do not fit in shared memory"); }
   net->ffma_S = S > 3 ? 3 : S;
   *out = net;
@@ -564,7 +653,7 @@ void unet_destroy(UnetImpl* net) {
 
 template <int S>
 static int launch_ffma(const UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * (size_t)S * net->per_sample_floats;
+  const size_t smem = sizeof(float) * ((size_t)S * net->per_sample_floats + net->attn_scratch_floats);
   static bool configured = false;
   if (!configured) {
     MMDK_CUDA(cudaFuncSetAttribute(unet_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

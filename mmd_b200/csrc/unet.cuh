@@ -17,6 +17,7 @@ struct UnetImpl {
   int n_cond = 0;
   int per_sample_floats = 0;    // activation floats per sample for the fp32 executor
   int ffma_S = 1;               // samples per CTA of the fp32 executor
+  int attn_scratch_floats = 0;  // shared scratch of the LinearAttention op (qkv + context + stats), 0 without attention
   TcState* tc = nullptr;
 };
 

@@ -83,6 +83,24 @@ def test_unet_tensor_core_matches_oracle(pair, dev, B):
         assert e < 5e-5
 
 
+def test_unet_linear_attention_fp32(dev):
+    """self_attention=True: Residual(PreNorm(LinearAttention)) after every level (layers.py:177-229), fp32 executor."""
+    import mmd_b200 as M
+    P = port.make_unet_params(seed=2, self_attention=True)
+    unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4), self_attention=True)
+    unet.load_state_dict(P, strict=True)
+    unet = unet.to(dev)
+    x = torch.randn(5, 64, 4, generator=torch.Generator().manual_seed(8))
+    for t in (0, 17):
+        ref = port.unet_forward(P, x, torch.full((5,), t, dtype=torch.long))
+        out = unet.forward_t(x.to(dev), t, precision="fp32")
+        e = rel_err(out, ref)
+        print(f"unet fp32 + linear attention t={t} rel_err={e:.3e}")
+        assert e < 2e-5
+    with pytest.raises(ValueError):
+        unet.forward_t(x.to(dev), 3, precision="f16x3")
+
+
 def test_unet_dim_mults_option1(dev):
     o = build_oracle("EnvEmpty2D", T=25, dim_mults=(1, 2, 4, 8))
     p = build_product(dev, "EnvEmpty2D", T=25, P=o["P"], dim_mults=(1, 2, 4, 8))
@@ -232,7 +250,9 @@ def test_run_inference_chain_free_running_tensor_core(dev, precision):
     fin = _per_traj(chain[-1], ref[-1])
     print(f"chain {precision} K={K} T={T} w_smooth=0: final rel L2 median={float(fin.median()):.2e} "
           f"p90={float(fin.quantile(0.9)):.2e} max={float(fin.max()):.2e}")
-    assert float(fin.median()) < 1e-4 and float(fin.quantile(0.9)) < 1e-3 and float(fin.max()) < 2e-2
+    # envelope: the oracle perturbed by 1.3e-6 / 3e-6 relative in eps deviates from itself on this very problem by
+    # median 9e-7 / 2e-6, p90 8e-6 / 2.5e-4, max 4.6e-2 / 2.1e-2 (branch flips compound over 51 guided steps)
+    assert float(fin.median()) < 1e-4 and float(fin.quantile(0.9)) < 1e-3 and float(fin.max()) < 1e-1
 
 
 @pytest.mark.parametrize("K,T,precision", [(8, 25, "fp32"), (16, 50, "fp32"), (8, 25, "f16x3"), (16, 100, "f16x3")])
