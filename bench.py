@@ -275,7 +275,8 @@ def run_gpu(args):
         B = R_PER_GPU * K
         achieved = B * UNET_FLOP_PER_SAMPLE / (unet_avg_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        launches_per_chain = n_steps * 2 + (math.ceil(0.5 * T) + N_EXTRA if R_total > 1 else 0)
+        n_unet_launches = 34 if args.precision == "f16x3" else 1   # pack_input + 33 fused conv layers, or the single fp32 kernel
+        launches_per_chain = n_steps * (n_unet_launches + 1) + (math.ceil(0.5 * T) + N_EXTRA if R_total > 1 else 0)
         cb_v, tu, tg, per_robot = (None, None, None, None)
         cores = os.cpu_count() or 1
         cpu = None
@@ -294,7 +295,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(sg_host.numel() * 4), "d2h_bytes_per_step": int(result_host.numel() * 4),
                     "note": "noise drawn on the device by torch.randn as the reference does"},
             "gpu_launches": launches_per_chain * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "unet_forward (" + args.precision + ")", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "TemporalUnet forward (" + args.precision + (": pack_input + 33 conv_tc_kernel launches)" if args.precision == "f16x3" else ": unet_ffma_kernel)"), "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                         f"dense TF32 is nominally half of it",
