@@ -93,7 +93,7 @@ def sinusoidal_table(n_steps, dim=32):
 class TemporalUnet(nn.Module):
     def __init__(self, n_support_points=None, state_dim=None, unet_input_dim=32, dim_mults=(1, 2, 4, 8),
                  time_emb_dim=32, self_attention=False, conditioning_embed_dim=4, conditioning_type=None,
-                 attention_num_heads=2, attention_dim_head=32, unet_precision="fp32", **kwargs):
+                 attention_num_heads=2, attention_dim_head=32, unet_precision="auto", **kwargs):
         super().__init__()
         if conditioning_type not in (None, "None"):
             # temporal_unet.py:44-58: 'concatenate'/'attention'/'default' need context models no planner builds
@@ -135,6 +135,27 @@ class TemporalUnet(nn.Module):
         self._handle_key = None
         self._keepalive = None
         self._time_table_steps = 1024
+
+    def tensor_core_supported(self):
+        """Whether the tcgen05 executor covers this network shape (unet_tc.cu build_tc): no LinearAttention, and every
+        level's (rows of a 7-sample tile) x channels fits the epilogue's register tiling."""
+        if self.self_attention or self.state_dim > 8:
+            return False
+        L = self.n_support_points
+        for i, m in enumerate(self.dim_mults):
+            C = self.unet_input_dim * m
+            n_mt = (7 * ((L >> i) + 2) + 127) // 128
+            if C not in (32, 64, 128) or n_mt * C not in (64, 128):
+                return False
+        return True
+
+    def resolve_precision(self, precision=None):
+        """'auto' (default): the tensor-core executor ("f16x3": FP16 hi/lo split, ~3e-6 relative on eps) when the shape is
+        supported, else the exact fp32 CUDA-core executor.  Both are native sm_100a kernels."""
+        p = precision or self.unet_precision
+        if p == "auto":
+            p = "f16x3" if self.tensor_core_supported() else "fp32"
+        return p
 
     # -- native handle ------------------------------------------------------------------------------------------
     def _invalidate(self):
@@ -217,6 +238,6 @@ class TemporalUnet(nn.Module):
         h = self.native()
         if out is None:
             out = torch.empty_like(x)
-        mode = _lib.UNET_MODES[precision or self.unet_precision]
+        mode = _lib.UNET_MODES[self.resolve_precision(precision)]
         _lib.check(lib.mmdk_unet_forward(h, mode, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
         return out

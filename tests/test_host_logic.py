@@ -86,3 +86,12 @@ def test_lower_env_values():
     assert e.gp_q11 == float(o.q_inv[0, 0]) and e.gp_q12 == float(o.q_inv[0, 2]) and e.gp_q22 == float(o.q_inv[2, 2])
     assert (e.nx, e.ny) == (400, 400) and abs(e.w_smooth - 8e-2) < 1e-8 and e.max_grad_norm == 1.0
     assert e.norm_range[2] == 4.0 and e.norm_min[2] == -2.0
+
+
+def test_executor_selection():
+    assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4)).resolve_precision() == "f16x3"
+    assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4, 8)).resolve_precision() == "fp32"
+    assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4),
+                          self_attention=True).resolve_precision() == "fp32"
+    u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4), unet_precision="fp32")
+    assert u.resolve_precision() == "fp32" and u.resolve_precision("f16x3") == "f16x3"
