@@ -56,3 +56,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_sass_contains_blackwell_native_instructions():
+    """The built library must carry tcgen05 / TMA / mbarrier SASS (B200_PROFILING.md: UTCHMMA, LDTM, UBLKCP), i.e. the
+    tensor-core executor is really in the binary the tests load."""
+    import shutil
+    import subprocess
+    import pytest
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTCBAR", "SYNCS"):
+        assert mnemonic in sass, f"{mnemonic} missing from libmmdk.so"
+    assert "HGMMA" not in sass  # no Hopper wgmma
