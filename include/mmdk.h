@@ -36,6 +36,7 @@ extern "C" {
 #define MMDK_MAX_LEVELS 4
 #define MMDK_MAX_HARD_ROWS 4
 #define MMDK_STATE_DIM 4
+#define MMDK_PEER_GRID_MAX 32
 
 /* Thread-local message of the last failing call. */
 const char* mmdk_last_error(void);
@@ -88,6 +89,11 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
  * dbg_dev [n_tiles, 16] int64 (slot 15 = SM id); op_index = -1 / dbg_dev = NULL switches it off. */
 int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream);
 
+/* Calibration (profiles/): n_ctas CTAs each issue n_iters back-to-back tcgen05.mma (M=128, N, K=16, kind::f16) and
+ * write {elapsed clock64 cycles, n_iters} to out_dev [n_ctas, 2] int64.  Run under ncu to read what
+ * sm__pipe_tensor_cycles_active reports for a loop that is 100% MMA issue. */
+int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Guide + DDPM step  (mmd/models/diffusion_models/guides.py:152-253, sample_functions.py:41-107,
  * diffusion_model_base.py:126-160, MPB/planners/costs/cost_functions.py, TR/environments/grid_map_sdf.py)
@@ -136,6 +142,15 @@ typedef struct {
   const int* peer_self_dev;     /* [n_groups] */
   int n_peers;
   float peer_radius, peer_weight;
+  /* Optional spatial hash of the peer table (mmdk_build_peer_hash): per waypoint a grid x grid uniform grid with
+   * cell >= peer_radius over [peer_grid_lo, peer_grid_lo + grid / peer_grid_inv_cell)^2 (clamped at the border).
+   * cell_start [H, grid*grid + 1] uint16, sorted [H, n_peers, 4] fp32 (x, y, peer index bits, 0).  With it the step
+   * kernel tests only the 3x3 cells around a waypoint instead of all n_peers rows (same exact in-radius test, so the
+   * same peers contribute).  NULL = brute-force scan of peers_dev. */
+  const uint16_t* peer_cell_start_dev;
+  const float* peer_sorted_dev;
+  int peer_grid;
+  float peer_grid_lo, peer_grid_inv_cell;
 } mmdk_groups;
 
 /* One evaluation of GuideManagerTrajectoriesWithVelocity.forward (guides.py:180-226): grad_dev [B,H,D] =
@@ -169,6 +184,12 @@ int mmdk_ddpm_step(const mmdk_guide_env* env, const mmdk_groups* groups, const m
  * unnormalise(x[g*K + rep_index])[:, :2] with the normaliser's clip rule applied to that group. */
 int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, int rep_index, const float* x_dev,
                        float* peers_out_dev, void* stream);
+
+/* Builds the spatial hash of a lock-step peer table peers_dev [n_peers, H, 2] (see mmdk_groups): replaces the
+ * reference's dense (n_constraints, B, H, 2) distance tensor (cost_functions.py:304-324) by an O(neighbours) lookup.
+ * grid <= MMDK_PEER_GRID_MAX; the caller chooses grid / lo / inv_cell with 1 / inv_cell >= peer_radius. */
+int mmdk_build_peer_hash(const float* peers_dev, int n_peers, int H, int grid, float grid_lo, float grid_inv_cell,
+                         uint16_t* cell_start_dev, float* sorted_dev, void* stream);
 
 /* apply_cross_conditioning (sample_functions.py:17-31) for one (m1, ind1) <- (m2, ind2) stitch of an ensemble:
  * x1[:, ind1, :] = min(x2[:, ind2, :] + rel, bnd); x2[:, ind2, :] = max(x1[:, ind1, :] - rel, -bnd). */

@@ -36,7 +36,9 @@ class Groups(C.Structure):
     _fields_ = [("n_groups", C.c_int), ("K", C.c_int), ("hard_vals_dev", C.c_void_p), ("hard_rows_dev", C.c_void_p),
                 ("obj_ptr_dev", C.c_void_p), ("obj_weight_dev", C.c_void_p), ("bucket_ptr_dev", C.c_void_p),
                 ("cons_dev", C.c_void_p), ("peers_dev", C.c_void_p), ("peer_self_dev", C.c_void_p),
-                ("n_peers", C.c_int), ("peer_radius", C.c_float), ("peer_weight", C.c_float)]
+                ("n_peers", C.c_int), ("peer_radius", C.c_float), ("peer_weight", C.c_float),
+                ("peer_cell_start_dev", C.c_void_p), ("peer_sorted_dev", C.c_void_p), ("peer_grid", C.c_int),
+                ("peer_grid_lo", C.c_float), ("peer_grid_inv_cell", C.c_float)]
 
 
 class StepScalars(C.Structure):
@@ -50,7 +52,7 @@ class StepScalars(C.Structure):
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
-    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_cross_condition",
+    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize",
 ]
 
@@ -81,9 +83,11 @@ def load():
     lib.mmdk_unet_cond_row.argtypes = [vp, i, vp, c_int_p, vp]
     lib.mmdk_unet_debug_tap.argtypes = [vp, i, vp, c_int_p, c_int_p, c_int_p, vp]
     lib.mmdk_unet_debug_timeline.argtypes = [vp, i, vp, vp]
+    lib.mmdk_debug_mma_calibrate.argtypes = [i, i, i, vp, vp]
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]
+    lib.mmdk_build_peer_hash.argtypes = [vp, i, i, i, f, f, vp, vp, vp]
     lib.mmdk_cross_condition.argtypes = [vp, vp, i, i, i, i, C.c_float * 4, C.c_float * 4, vp]
     lib.mmdk_q_sample.argtypes = [vp, vp, f, f, i64, vp, vp]
     lib.mmdk_cell_index.argtypes = [C.POINTER(GuideEnv), vp, i64, vp, vp]

@@ -96,4 +96,9 @@ int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_
   return unet_tc_timeline(net->impl, op_index, dbg_dev, (cudaStream_t)stream);
 }
 
+int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, void* stream) {
+  if (!out_dev) return fail(MMDK_EINVAL, "null argument");
+  return mma_calibrate(N, n_iters, n_ctas, out_dev, (cudaStream_t)stream);
+}
+
 }  // extern "C"

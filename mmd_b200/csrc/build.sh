@@ -6,10 +6,18 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH --expt-relaxed-constexpr"
 mkdir -p ../_build
-$NVCC $COMMON -c api.cu -o ../_build/api.o "$@" &
-$NVCC $COMMON -c unet.cu -o ../_build/unet.o "$@" &
-$NVCC $COMMON -c unet_tc.cu -o ../_build/unet_tc.o "$@" &
-$NVCC $COMMON -fmad=false -c guide.cu -o ../_build/guide.o "$@" &
-wait
-$NVCC -shared $ARCH -o ../libmmdk.so ../_build/api.o ../_build/unet.o ../_build/unet_tc.o ../_build/guide.o -lcudart
+SRCS="api unet unet_tc guide"
+pids=()
+for f in $SRCS; do
+  rm -f ../_build/$f.o            # a failed compile must never leave a stale object for the link step
+  extra=""
+  # guide.cu reproduces the reference's op-by-op fp32 arithmetic: no FMA contraction
+  if [ "$f" = guide ]; then extra="-fmad=false"; fi
+  $NVCC $COMMON $extra -c $f.cu -o ../_build/$f.o "$@" &
+  pids+=($!)
+done
+for pid in "${pids[@]}"; do wait "$pid"; done   # `wait <pid>` propagates each compile's exit status to set -e
+OBJS=""
+for f in $SRCS; do OBJS="$OBJS ../_build/$f.o"; done
+$NVCC -shared $ARCH -o ../libmmdk.so $OBJS -lcudart
 echo "built $(cd .. && pwd)/libmmdk.so"

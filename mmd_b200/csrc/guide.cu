@@ -57,6 +57,16 @@ __device__ __forceinline__ void cell_index(const mmdk_guide_env& e, float px, fl
   iy = (int)fy;
 }
 
+// cell of the lock-step peer hash (uniform grid over [lo, lo + G / inv_cell)^2, clamped): used by the build kernel and
+// by the query with the SAME fp32 expressions, so a point always lands in the cell the builder put it in
+__device__ __forceinline__ void peer_cell(float lo, float inv_cell, int G, float px, float py, int& cx, int& cy) {
+  float fx = floorf((px - lo) * inv_cell), fy = floorf((py - lo) * inv_cell);
+  fx = fminf(fmaxf(fx, 0.f), (float)(G - 1));
+  fy = fminf(fmaxf(fy, 0.f), (float)(G - 1));
+  cx = (int)fx;
+  cy = (int)fy;
+}
+
 template <bool TAPS>
 __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
   extern __shared__ float4 s_xu[];   // [spc][H] unnormalised states of this CTA's samples
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
 
   // lock-step peers: constant for the whole launch -> one coalesced copy into shared memory, 20 x reuse
   float2* s_peers = reinterpret_cast<float2*>(s_xu + (size_t)a.spc * H);
-  if (a.grp.peers_dev && a.peers_in_smem) {
+  if (a.grp.peers_dev && a.peers_in_smem && !a.grp.peer_cell_start_dev) {
     const float2* gp = reinterpret_cast<const float2*>(a.grp.peers_dev);
     for (int i = tid; i < a.grp.n_peers * H; i += blockDim.x) s_peers[i] = __ldg(gp + i);
     __syncthreads();
@@ -240,20 +250,45 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
       emit(gk, a.grp.obj_weight_dev[o]);
     }
     // ---- lock-step peers: one implicit soft CostConstraint with ranges (h, h+1) ----------------------------------
+    // The in/out-of-radius decision is the reference's exact fp32 test (cost_functions.py:316-318) in both paths; the
+    // hashed path only restricts WHICH peers are tested: per waypoint the [n_peers] table is bucketed into a uniform grid
+    // with cell >= radius (mmdk_build_peer_hash), so the 3x3 cells around the waypoint hold every peer within the radius.
     if (a.grp.peers_dev) {
       float gk[4] = {0.f, 0.f, 0.f, 0.f};
       const float r = a.grp.peer_radius;
       const float r2_far = r * r * 1.0001f;
-      const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev)) + h;
+      if (a.grp.peer_cell_start_dev) {
+        const int G = a.grp.peer_grid;
+        const unsigned short* cs = a.grp.peer_cell_start_dev + (size_t)h * (G * G + 1);
+        const float4* sp = reinterpret_cast<const float4*>(a.grp.peer_sorted_dev) + (size_t)h * a.grp.n_peers;
+        int cx, cy;
+        peer_cell(a.grp.peer_grid_lo, a.grp.peer_grid_inv_cell, G, xu[0], xu[1], cx, cy);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G - 1);
+        const int y0 = max(cy - 1, 0), y1 = min(cy + 1, G - 1);
+        for (int yy = y0; yy <= y1; ++yy) {
+          const int e0 = cs[yy * G + x0], e1 = cs[yy * G + x1 + 1];
+          for (int e = e0; e < e1; ++e) {
+            const float4 q = __ldg(sp + e);
+            if (__float_as_int(q.z) == self_peer) continue;
+            float dx = xu[0] - q.x, dy = xu[1] - q.y;
+            float d2 = dx * dx + dy * dy;
+            if (d2 > r2_far) continue;
+            float dist = sqrtf(d2);
+            if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
+          }
+        }
+      } else {
+        const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev)) + h;
 #pragma unroll 4
-      for (int j = 0; j < a.grp.n_peers; ++j, pq += H) {
-        if (j == self_peer) continue;
-        const float2 q = *pq;
-        float dx = xu[0] - q.x, dy = xu[1] - q.y;
-        float d2 = dx * dx + dy * dy;
-        if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
-        float dist = sqrtf(d2);
-        if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
+        for (int j = 0; j < a.grp.n_peers; ++j, pq += H) {
+          if (j == self_peer) continue;
+          const float2 q = *pq;
+          float dx = xu[0] - q.x, dy = xu[1] - q.y;
+          float d2 = dx * dx + dy * dy;
+          if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
+          float dist = sqrtf(d2);
+          if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
+        }
       }
       emit(gk, a.grp.peer_weight);
     }
@@ -312,17 +347,28 @@ static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  static bool big_smem_set = false;
-  if (smem > 48 * 1024 && !big_smem_set) {
-    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16384));
-    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16384));
-    big_smem_set = true;
-  }
-  static bool np_set = false;
-  if (args.cpg > 8 && !np_set) {
-    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    np_set = true;
+  // Function attributes are per device: configure once per (device) and always opt in to the device maximum, so
+  // that static + dynamic shared memory can never straddle the 48 KiB default (round-1 N=2 crash: exactly 48 KiB
+  // dynamic + 128 B static) and a second device in the same process gets its own opt-in.
+  {
+    int dev = 0;
+    MMDK_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64) return fail(MMDK_EINVAL, "device index out of range");
+    if (!configured[dev]) {
+      int max_optin = 0;
+      MMDK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      cudaFuncAttributes fa{};
+      MMDK_CUDA(cudaFuncGetAttributes(&fa, ddpm_step_kernel<false>));
+      const int dyn_max = max_optin - (int)fa.sharedSizeBytes;
+      MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+      MMDK_CUDA(cudaFuncGetAttributes(&fa, ddpm_step_kernel<true>));
+      MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     max_optin - (int)fa.sharedSizeBytes));
+      MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      MMDK_CUDA(cudaFuncSetAttribute(ddpm_step_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      configured[dev] = true;
+    }
   }
   cudaError_t e = taps ? cudaLaunchKernelEx(&cfg, ddpm_step_kernel<true>, args)
                        : cudaLaunchKernelEx(&cfg, ddpm_step_kernel<false>, args);
@@ -342,8 +388,10 @@ static int plan_step(StepArgs& a) {
   spc = (K + cpg - 1) / cpg;
   a.spc = spc;
   a.cpg = cpg;
-  a.peers_in_smem = (a.grp.peers_dev != nullptr &&
+  a.peers_in_smem = (a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev == nullptr &&
                      sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 200 * 1024) ? 1 : 0;
+  if (a.grp.peer_cell_start_dev && (a.grp.peer_grid < 1 || a.grp.peer_grid > MMDK_PEER_GRID_MAX || !a.grp.peer_sorted_dev))
+    return fail(MMDK_EINVAL, "peer hash: bad grid size or missing sorted table");
   return MMDK_OK;
 }
 
@@ -367,6 +415,38 @@ __global__ void publish_peers_kernel(mmdk_guide_env E, int K, int H, int rep, co
     if (flag) v = fminf(fmaxf(v, -1.f), 1.f);
     v = (v + 1.f) / 2.f;
     out[((size_t)g * H + h) * 2 + d] = v * E.norm_range[d] + E.norm_min[d];
+  }
+}
+
+// Lock-step peer hash: one CTA per waypoint h.  Stable counting sort of the [n_peers] positions of waypoint h into a
+// G x G uniform grid (cell >= peer radius): cell_start [H][G*G+1] (uint16), sorted [H][n_peers] float4 (x, y, index, 0).
+// Stable (peers of a cell stay in index order), so the query visits candidates in a deterministic order.
+__global__ void build_peer_hash_kernel(const float* __restrict__ peers, int n_peers, int H, int G, float lo, float inv_cell,
+                                       unsigned short* __restrict__ cell_start, float4* __restrict__ sorted) {
+  extern __shared__ int s_hash[];            // [G*G+1] counts / offsets, then [n_peers] cell of every peer
+  int* s_cnt = s_hash;
+  int* s_cell = s_hash + G * G + 1;
+  const int h = blockIdx.x, nc = G * G;
+  for (int i = threadIdx.x; i <= nc; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_peers; j += blockDim.x) {
+    const float2 q = reinterpret_cast<const float2*>(peers)[(size_t)j * H + h];
+    int cx, cy;
+    peer_cell(lo, inv_cell, G, q.x, q.y, cx, cy);
+    const int c = cy * G + cx;
+    s_cell[j] = c;
+    atomicAdd(&s_cnt[c + 1], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) for (int i = 0; i < nc; ++i) s_cnt[i + 1] += s_cnt[i];   // <= 1025 entries
+  __syncthreads();
+  for (int i = threadIdx.x; i <= nc; i += blockDim.x) cell_start[(size_t)h * (nc + 1) + i] = (unsigned short)s_cnt[i];
+  for (int j = threadIdx.x; j < n_peers; j += blockDim.x) {
+    const int c = s_cell[j];
+    int rank = 0;
+    for (int k = 0; k < j; ++k) rank += (s_cell[k] == c);
+    const float2 q = reinterpret_cast<const float2*>(peers)[(size_t)j * H + h];
+    sorted[(size_t)h * n_peers + s_cnt[c] + rank] = make_float4(q.x, q.y, __int_as_float(j), 0.f);
   }
 }
 
@@ -521,6 +601,18 @@ int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, in
   if (rep_index < 0 || rep_index >= K) return fail(MMDK_EINVAL, "rep_index out of range");
   publish_peers_kernel<<<n_groups, 256, 0, (cudaStream_t)stream>>>(*env, K, H, rep_index, x_dev, peers_out_dev);
   return check_cuda(cudaGetLastError(), "publish_peers_kernel");
+}
+
+int mmdk_build_peer_hash(const float* peers_dev, int n_peers, int H, int grid, float grid_lo, float grid_inv_cell,
+                         uint16_t* cell_start_dev, float* sorted_dev, void* stream) {
+  if (!peers_dev || !cell_start_dev || !sorted_dev) return fail(MMDK_EINVAL, "null argument");
+  if (grid < 1 || grid > MMDK_PEER_GRID_MAX) return fail(MMDK_EINVAL, "peer hash grid out of range");
+  if (n_peers < 1 || n_peers > 65535 || H < 1) return fail(MMDK_EINVAL, "peer hash: n_peers must be in [1, 65535]");
+  const size_t smem = sizeof(int) * ((size_t)grid * grid + 1 + n_peers);
+  if (smem > 48 * 1024) return fail(MMDK_EINVAL, "peer hash: fleet too large for the single-CTA-per-waypoint builder");
+  build_peer_hash_kernel<<<H, 256, smem, (cudaStream_t)stream>>>(peers_dev, n_peers, H, grid, grid_lo, grid_inv_cell,
+                                                              cell_start_dev, reinterpret_cast<float4*>(sorted_dev));
+  return check_cuda(cudaGetLastError(), "build_peer_hash_kernel");
 }
 
 int mmdk_cross_condition(float* x1_dev, float* x2_dev, int B, int H, int ind1, int ind2, const float rel[4],

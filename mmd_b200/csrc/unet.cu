@@ -590,8 +590,13 @@ int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* n
   rc = lower(real, *cfg, net->ops, conds, net->per_sample_floats, net->n_cond);
   if (rc != MMDK_OK) { std::string e = real.err; unet_destroy(net); return fail(rc, e); }
 
-  MMDK_CUDA(cudaMalloc(&net->ops_dev, sizeof(Op) * net->ops.size()));
-  MMDK_CUDA(cudaMemcpyAsync(net->ops_dev, net->ops.data(), sizeof(Op) * net->ops.size(), cudaMemcpyHostToDevice, stream));
+#define MMDK_CUDA_NET(call)                                                     \
+  do {                                                                          \
+    int _rc = ::mmdk::check_cuda((call), #call);                                \
+    if (_rc != MMDK_OK) { unet_destroy(net); return _rc; }                      \
+  } while (0)
+  MMDK_CUDA_NET(cudaMalloc(&net->ops_dev, sizeof(Op) * net->ops.size()));
+  MMDK_CUDA_NET(cudaMemcpyAsync(net->ops_dev, net->ops.data(), sizeof(Op) * net->ops.size(), cudaMemcpyHostToDevice, stream));
 
   // cond table for all t
   const int Tn = cfg->n_diffusion_steps;
@@ -621,14 +626,25 @@ int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* n
     tp[i] = it->second.first;
   }
   CondLayer* cl_dev = nullptr;
-  MMDK_CUDA(cudaMalloc(&cl_dev, sizeof(CondLayer) * cl.size()));
-  MMDK_CUDA(cudaMemcpyAsync(cl_dev, cl.data(), sizeof(CondLayer) * cl.size(), cudaMemcpyHostToDevice, stream));
-  MMDK_CUDA(cudaMalloc(&net->cond_table, sizeof(float) * (size_t)Tn * net->n_cond));
+  MMDK_CUDA_NET(cudaMalloc(&cl_dev, sizeof(CondLayer) * cl.size()));
+  if (check_cuda(cudaMemcpyAsync(cl_dev, cl.data(), sizeof(CondLayer) * cl.size(), cudaMemcpyHostToDevice, stream),
+                 "cudaMemcpyAsync(cond layers)") != MMDK_OK ||
+      check_cuda(cudaMalloc(&net->cond_table, sizeof(float) * (size_t)Tn * net->n_cond), "cudaMalloc(cond table)") != MMDK_OK) {
+    cudaFree(cl_dev);
+    unet_destroy(net);
+    return MMDK_ECUDA;
+  }
   time_embed_kernel<<<Tn, 128, 0, stream>>>(sc->second.first, tp[0], tp[1], tp[2], tp[3], cl_dev, (int)cl.size(),
                                             cfg->time_emb_dim, net->n_cond, net->cond_table);
-  MMDK_CUDA(cudaGetLastError());
-  MMDK_CUDA(cudaStreamSynchronize(stream));  // cl (host vector) and cl_dev must outlive the kernel
-  cudaFree(cl_dev);
+  {
+    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(stream);  // cl (host vector) and cl_dev must outlive the kernel
+    cudaFree(cl_dev);
+    if (check_cuda(e1, "time_embed_kernel") != MMDK_OK || check_cuda(e2, "cudaStreamSynchronize") != MMDK_OK) {
+      unet_destroy(net);
+      return MMDK_ECUDA;
+    }
+  }
 
   // executor configuration: as many samples per CTA as shared memory allows (<= 4)
   int dev = 0, max_smem = 0;
@@ -654,10 +670,17 @@ void unet_destroy(UnetImpl* net) {
 template <int S>
 static int launch_ffma(const UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream) {
   const size_t smem = sizeof(float) * ((size_t)S * net->per_sample_floats + net->attn_scratch_floats);
-  static bool configured = false;
-  if (!configured) {
-    MMDK_CUDA(cudaFuncSetAttribute(unet_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  {  // function attributes are per device: opt in to the device maximum once per device
+    int dev = 0;
+    MMDK_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64) return fail(MMDK_EINVAL, "device index out of range");
+    if (!configured[dev]) {
+      int max_optin = 0;
+      MMDK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      MMDK_CUDA(cudaFuncSetAttribute(unet_ffma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+      configured[dev] = true;
+    }
   }
   const int grid = (B + S - 1) / S;
   unet_ffma_kernel<S><<<grid, 256, smem, stream>>>(net->ops_dev, (int)net->ops.size(), net->blob,

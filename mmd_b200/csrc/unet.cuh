@@ -30,6 +30,7 @@ int unet_forward_ffma(const UnetImpl* net, const float* x, int B, int t, float* 
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream);
 void unet_tc_release(UnetImpl* net);
 int unet_tc_timeline(UnetImpl* net, int op_index, long long* dbg_dev, cudaStream_t stream);
+int mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, cudaStream_t stream);
 int unet_tc_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out, cudaStream_t stream);
 
 }  // namespace mmdk

@@ -587,6 +587,53 @@ __global__ void unpack_image_kernel(const uint8_t* __restrict__ img, uint32_t ti
   out[idx] = __half2float(base[o]) + __half2float(base[plane + o]);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// calibration: a pure tcgen05.mma loop (M=128, N, K=16, kind::f16, SS mode, operands = whatever is in shared memory) to
+// calibrate ncu's sm__pipe_tensor_cycles_active against the issue model (N/2 cycles per instruction at M=128) and to
+// measure the real cycles per MMA for every N the UNet uses.  out[blockIdx.x] = {cycles, n_mma}.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mma_calibrate_kernel(int N, int n_iters, int a_rows, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (a_rows * 16 * 2 + N * 16 * 2) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem), b0 = a0 + (uint32_t)a_rows * 32u;
+    const uint32_t a_lbo = (uint32_t)a_rows * 16u;
+    const long long t0 = clock64();
+    for (int it = 0; it < n_iters; ++it) {
+      // walk the A start address like the conv taps do (16-byte row shifts), 2 accumulators alternating
+      const uint64_t da = make_desc(a0 + (uint32_t)((it % 5) * 16), a_lbo, 128);
+      const uint64_t db = make_desc(b0, (uint32_t)N * 16u, 128);
+      tc_mma_f16(tmem_base + (uint32_t)((it & 1) * 256), da, db, idesc, it >= 2 ? 1u : 0u);
+    }
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = n_iters;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -860,6 +907,14 @@ int unet_tc_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out,
   const int n = st->B * im.C * im.L;
   unpack_image_kernel<<<(n + 255) / 256, 256, 0, stream>>>(im.dev, im.tile_bytes, st->B, im.C, im.L, im.rows, out);
   return check_cuda(cudaGetLastError(), "unpack_image_kernel");
+}
+
+int mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, cudaStream_t stream) {
+  if (N < 16 || N > 256 || (N & 15) || n_iters < 2 || n_ctas < 1) return fail(MMDK_EINVAL, "mma_calibrate: bad arguments");
+  const int a_rows = 128 + 8;
+  const size_t smem = (size_t)a_rows * 32 + (size_t)N * 32 + 128;
+  mma_calibrate_kernel<<<n_ctas, 128, smem, stream>>>(N, n_iters, a_rows, out_dev);
+  return check_cuda(cudaGetLastError(), "mma_calibrate_kernel");
 }
 
 }  // namespace mmdk

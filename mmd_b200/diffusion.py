@@ -129,7 +129,7 @@ def _run_step(guide, x, hard_conds_per_group, K, eps, noise, chain_slot, sc, con
 
 
 def lower_for_step(guide, n_groups, K, H, device, hard_conds_per_group, constraints_per_group=None, peers=None,
-                   peer_self=None, peer_radius=0.0, peer_weight=0.0):
+                   peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None):
     """(mmdk_guide_env, mmdk_groups, keepalive) for a batch of `n_groups` planner calls of K samples."""
     if guide is not None:
         env, keep = guide.lower_env(device)
@@ -141,7 +141,7 @@ def lower_for_step(guide, n_groups, K, H, device, hard_conds_per_group, constrai
         constraints_per_group = [([], [])] * n_groups
     grp, keep2 = GuideManagerTrajectoriesWithVelocity.lower_groups(
         helper, n_groups, K, H, device, constraints_per_group, hard_conds_per_group, peers, peer_self, peer_radius,
-        peer_weight)
+        peer_weight, peer_hash)
     return env, grp, keep + keep2
 
 

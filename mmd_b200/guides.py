@@ -190,7 +190,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         return env, keep
 
     def lower_groups(self, n_groups, K, H, device, constraints_per_group, hard_conds_per_group, peers=None,
-                     peer_self=None, peer_radius=0.0, peer_weight=0.0):
+                     peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None):
         """mmdk_groups for `n_groups` planner calls of K samples.  constraints_per_group[g] = (costs, weights);
         hard_conds_per_group[g] = {row: tensor[D]} (normalised) or None."""
         grp = _lib.Groups()
@@ -239,10 +239,46 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
             grp.peers_dev, grp.peer_self_dev = peers.data_ptr(), peer_self.data_ptr()
             grp.n_peers = peers.shape[0]
             grp.peer_radius, grp.peer_weight = float(peer_radius), float(peer_weight)
+            if peer_hash is not None:
+                keep.append(peer_hash)
+                grp.peer_cell_start_dev = peer_hash.cell_start.data_ptr()
+                grp.peer_sorted_dev = peer_hash.sorted.data_ptr()
+                grp.peer_grid, grp.peer_grid_lo = peer_hash.grid, peer_hash.lo
+                grp.peer_grid_inv_cell = peer_hash.inv_cell
+            else:
+                grp.peer_cell_start_dev = None
+                grp.peer_sorted_dev = None
         else:
             grp.peers_dev = None
             grp.n_peers = 0
+            grp.peer_cell_start_dev = None
+            grp.peer_sorted_dev = None
         return grp, keep
+
+
+class PeerHash:
+    """Per-waypoint uniform-grid hash of a lock-step peer table [n_peers, H, 2] (include/mmdk.h mmdk_build_peer_hash).
+    Cell size >= radius (a hair above it, so fp32 rounding of the cell coordinate can never push a peer within the
+    radius two cells away); the grid covers [-1.2, 1.2]^2 and clamps at its border (clamping is 1-Lipschitz, so the
+    3x3 neighbourhood stays sufficient outside the box too)."""
+    SPAN, LO, GRID_MAX = 2.4, -1.2, 32
+
+    def __init__(self, n_peers, H, radius, device):
+        import math
+        self.n_peers, self.H = int(n_peers), int(H)
+        self.grid = max(1, min(self.GRID_MAX, int(math.floor(self.SPAN / (float(radius) * 1.001)))))
+        self.lo = self.LO
+        self.inv_cell = self.grid / self.SPAN
+        assert 1.0 / self.inv_cell >= float(radius)
+        self.cell_start = torch.zeros(H, self.grid * self.grid + 1, dtype=torch.int16, device=device)
+        self.sorted = torch.zeros(H, self.n_peers, 4, dtype=torch.float32, device=device)
+
+    def build(self, peers):
+        assert peers.shape == (self.n_peers, self.H, 2) and peers.is_contiguous()
+        _lib.check(_lib.lib().mmdk_build_peer_hash(_lib.ptr(peers), self.n_peers, self.H, self.grid, self.lo,
+                                                   self.inv_cell, _lib.ptr(self.cell_start), _lib.ptr(self.sorted),
+                                                   _lib.stream_ptr()))
+        return self
 
 
 def _is_empty_object_field(df):

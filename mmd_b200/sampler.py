@@ -19,6 +19,7 @@ import torch
 
 from . import _lib
 from .diffusion import GaussianDiffusionModel, _run_step, lower_for_step
+from .guides import PeerHash
 
 
 def shard_robots(n_robots_total: int, world_size: int, rank: int):
@@ -50,7 +51,7 @@ def gather_peers(peers_local: torch.Tensor, n_robots_total: int, group=None) -> 
 class MultiRobotSampler:
     def __init__(self, model: GaussianDiffusionModel, guide, n_guide_steps=20, t_start_guide=None, noise_std=0.5,
                  n_diffusion_steps_without_noise=1, peer_radius=2.4 * 0.05, peer_weight=2e-2, rep_index=0,
-                 process_group=None):
+                 process_group=None, use_peer_hash=True):
         self.model, self.guide = model, guide
         self.n_guide_steps = n_guide_steps
         T = model.n_diffusion_steps
@@ -59,6 +60,7 @@ class MultiRobotSampler:
         self.n_extra = n_diffusion_steps_without_noise
         self.peer_radius, self.peer_weight, self.rep_index = peer_radius, peer_weight, rep_index
         self.pg = process_group
+        self.use_peer_hash = use_peer_hash  # False: brute-force scan of the peer table (kept for the equality test)
 
     @torch.no_grad()
     def sample(self, hard_conds_l: Sequence[dict], n_samples: int, noise: Optional[torch.Tensor] = None,
@@ -95,17 +97,19 @@ class MultiRobotSampler:
         if return_chain:
             chain[0].copy_(x)
 
-        peers = peer_self = peers_local = None
+        peers = peer_self = peers_local = peer_hash = None
         if mode == "lockstep":
             peers = torch.zeros(R_total, H, 2, device=dev)
             peers_local = peers[robot_offset:robot_offset + R] if not distributed else torch.zeros(R, H, 2, device=dev)
             peer_self = torch.arange(robot_offset, robot_offset + R, dtype=torch.int32, device=dev)
+            if self.use_peer_hash and R_total > 1:
+                peer_hash = PeerHash(R_total, H, self.peer_radius, dev)
         elif mode != "independent":
             raise ValueError("mode must be 'lockstep' or 'independent'")
         if constraints_l is None:
             constraints_l = [([], [])] * R
         env, grp, keep = lower_for_step(guide, R, K, H, dev, list(hard_conds_l), list(constraints_l), peers, peer_self,
-                                        self.peer_radius, self.peer_weight)
+                                        self.peer_radius, self.peer_weight, peer_hash)
         eps = torch.empty_like(x)
         k = 1
         for i in reversed(range(-self.n_extra, T)):
@@ -115,6 +119,8 @@ class MultiRobotSampler:
                                                   _lib.ptr(peers_local), _lib.stream_ptr()))
                 if distributed:
                     peers.copy_(gather_peers(peers_local, R_total, self.pg))
+                if peer_hash is not None:
+                    peer_hash.build(peers)
             t = max(i, 0)
             model.model.forward_t(x, t, precision=model.unet_precision, out=eps)
             sc = model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True)

@@ -147,6 +147,16 @@ class TemporalUnet(nn.Module):
             n_mt = (7 * ((L >> i) + 2) + 127) // 128
             if C not in (32, 64, 128) or n_mt * C not in (64, 128):
                 return False
+        # the output-side ops of build_tc: up-path blocks run with the channel count of the level above, the final
+        # conv block (unet_input_dim channels) and the final 1x1 conv (N = 16) run at full resolution
+        for i in range(1, len(self.dim_mults)):
+            C_up = self.unet_input_dim * self.dim_mults[i - 1]
+            n_mt = (7 * ((L >> i) + 2) + 127) // 128
+            if n_mt * C_up not in (64, 128):
+                return False
+        n_mt0 = (7 * (L + 2) + 127) // 128
+        if n_mt0 * 16 != 64 or n_mt0 * self.unet_input_dim not in (64, 128):
+            return False
         return True
 
     def resolve_precision(self, precision=None):
@@ -195,7 +205,11 @@ class TemporalUnet(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.MMDKError("TemporalUnet parameters must live on a CUDA device (no CPU path)")
-        key = (dev, self._time_table_steps)
+        # keyed on every parameter's version counter too: load_state_dict through a PARENT module
+        # (GaussianDiffusionModel.load_state_dict recurses via _load_from_state_dict and never calls this class's
+        # override) and in-place updates (p.data.copy_, optimiser steps) bump `_version`, so stale packed weights on
+        # the device can never be used silently
+        key = (dev, self._time_table_steps, tuple((p.data_ptr(), p._version) for p in self.parameters()))
         if self._handle is not None and self._handle_key == key:
             return self._handle
         self._release()

@@ -34,7 +34,7 @@ def test_struct_layouts_match_header_field_order():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int|void)\s*\*?\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int|void|uint16_t|uint8_t|int64_t|int32_t)\s*\*?\s*", "", decl)
             for f in decl.split(","):
                 fields.append(re.sub(r"\[.*\]", "", f).strip().lstrip("*").strip())
         assert fields == [f[0] for f in struct._fields_], cname

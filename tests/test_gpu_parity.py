@@ -465,3 +465,42 @@ def test_diffusions_ensemble_two_tiles(dev):
         e = _per_traj(out[m], ref[m][-1])
         print(f"ensemble tile {m}: median={float(e.median()):.2e} max={float(e.max()):.2e}")
         assert float(e.median()) < 1e-4 and float(e.max()) < 2e-2
+
+
+@pytest.mark.parametrize("n_peers", [31, 32, 63, 64, 65, 128, 256])
+def test_peer_table_sizes_cross_smem_boundary(pair, dev, n_peers):
+    """Round-1 N=2 crash: at K=128 the brute-force path stages the [n_peers,64,2] table in shared memory; 64 rows made
+    the dynamic size exactly 48 KiB (+128 B static) without the opt-in.  Sweep the boundary with the cluster (K=128)
+    launch shape, on both peer paths (brute force in shared memory, spatial hash), and pin a slice against the oracle."""
+    import ctypes as C
+    from mmd_b200 import _lib
+    from mmd_b200.diffusion import lower_for_step
+    from mmd_b200.guides import PeerHash
+    o, p = pair
+    R, K = 2, 128
+    g = torch.Generator().manual_seed(n_peers)
+    x = torch.randn(R * K, 64, 4, generator=g) * 0.3
+    xd = x.to(dev)
+    peers_h = torch.rand(n_peers, 64, 2, generator=g) * 1.2 - 0.6
+    peers_h[5] = torch.rand(64, 2, generator=g) * 3.0 - 1.5   # one robot wandering outside the hash box (clamped cells)
+    peers = peers_h.to(dev).contiguous()
+    peer_self = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+    out = {}
+    for name, ph in (("brute", None), ("hash", PeerHash(n_peers, 64, 0.12, dev).build(peers))):
+        env, grp, keep = lower_for_step(p["guide"], R, K, 64, dev, [None] * R, None, peers, peer_self, 0.12, 2e-2, ph)
+        grad = torch.empty_like(xd)
+        _lib.check(_lib.lib().mmdk_guide_grad(C.byref(env), C.byref(grp), 64, _lib.ptr(xd), _lib.ptr(grad), None, 0,
+                                              _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        out[name] = grad.cpu()
+    assert torch.isfinite(out["brute"]).all()
+    assert max_err(out["hash"], out["brute"]) < 1e-6   # same peers contribute; only the summation order may differ
+    hh = torch.arange(64, dtype=torch.float32).repeat(n_peers - 1)
+    for r in range(R):
+        qs = torch.cat([peers_h[j] for j in range(n_peers) if j != r], 0)
+        o["guide"].extra = [port.Constraint(qs, torch.stack((hh, hh + 1), -1), torch.full((qs.shape[0],), 0.12), True, 2e-2)]
+        sl = slice(r * K, r * K + 2)   # no element leaves [-1, 1]: the clip decision of the slice equals the group's
+        assert float(x[r * K:(r + 1) * K].abs().max()) < 1.0
+        ref = o["guide"](x[sl])
+        o["guide"].extra = []
+        assert max_err(out["hash"][sl], ref) < 1e-6, (n_peers, r)
