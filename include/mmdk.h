@@ -70,7 +70,9 @@ void mmdk_unet_destroy(mmdk_unet* net);
 
 /* Numerical mode of the conv contractions. */
 #define MMDK_UNET_FP32 0     /* CUDA-core FFMA, fp32 throughout (exact-parity mode) */
-#define MMDK_UNET_F16X3 1    /* tcgen05 kind::f16, operands split hi+lo in FP16 (3 MMAs), fp32 accumulate in TMEM */
+#define MMDK_UNET_F16X3 1    /* tcgen05 kind::f16, operands split hi+lo in FP16 (3 MMAs), fp32 accumulate in TMEM:
+                                ONE persistent launch per forward (unet_fused.cu) */
+#define MMDK_UNET_F16X3_LAYERS 2 /* same arithmetic, one launch per layer (unet_tc.cu; round-1 executor, A/B baseline) */
 
 /* eps = TemporalUnet.forward(x, t, context=None) for an integer timestep t shared by the batch
  * (temporal_unet.py:121-174; make_timesteps, diffusion_model_base.py:27-29).  x_dev, eps_dev: [B, H, D]. */

@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libmmdk.so")
 
 MMDK_OK, MMDK_EINVAL, MMDK_ECUDA, MMDK_ENOMEM = 0, 1, 2, 3
 MAX_LEVELS, MAX_HARD_ROWS, STATE_DIM = 4, 4, 4
-UNET_FP32, UNET_F16X3 = 0, 1
-UNET_MODES = {"fp32": UNET_FP32, "f16x3": UNET_F16X3, "tc": UNET_F16X3}
+UNET_FP32, UNET_F16X3, UNET_F16X3_LAYERS = 0, 1, 2
+UNET_MODES = {"fp32": UNET_FP32, "f16x3": UNET_F16X3, "tc": UNET_F16X3, "f16x3_layers": UNET_F16X3_LAYERS}
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)

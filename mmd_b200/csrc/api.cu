@@ -70,7 +70,9 @@ int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B,
   if (B <= 0) return MMDK_OK;
   if (t < 0 || t >= net->impl->cfg.n_diffusion_steps) return fail(MMDK_EINVAL, "timestep out of range");
   if (mode == MMDK_UNET_FP32) return unet_forward_ffma(net->impl, x_dev, B, t, eps_dev, (cudaStream_t)stream);
-  if (mode == MMDK_UNET_F16X3) return unet_forward_tc(net->impl, mode, x_dev, B, t, eps_dev, (cudaStream_t)stream);
+  net->impl->last_mode = mode;
+  if (mode == MMDK_UNET_F16X3) return unet_forward_fused(net->impl, x_dev, B, t, eps_dev, (cudaStream_t)stream);
+  if (mode == MMDK_UNET_F16X3_LAYERS) return unet_forward_tc(net->impl, mode, x_dev, B, t, eps_dev, (cudaStream_t)stream);
   return fail(MMDK_EINVAL, "unknown UNet mode");
 }
 
@@ -88,7 +90,8 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
                         void* stream) {
   if (!net) return fail(MMDK_EINVAL, "null argument");
   if (n_ops_out) *n_ops_out = (int)net->impl->ops.size();
-  return unet_tc_tap(net->impl, op_index, out_dev, c_out, l_out, (cudaStream_t)stream);
+  if (net->impl->last_mode == MMDK_UNET_F16X3_LAYERS) return unet_tc_tap(net->impl, op_index, out_dev, c_out, l_out, (cudaStream_t)stream);
+  return unet_fused_tap(net->impl, op_index, out_dev, c_out, l_out, (cudaStream_t)stream);
 }
 
 int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream) {

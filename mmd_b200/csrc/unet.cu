@@ -664,6 +664,7 @@ void unet_destroy(UnetImpl* net) {
   cudaFree(net->ops_dev);
   cudaFree(net->cond_table);
   unet_tc_release(net);
+  unet_fused_release(net);
   delete net;
 }
 

@@ -1,11 +1,13 @@
 #pragma once
+#include <map>
 #include <vector>
 
 #include "common.cuh"
 
 namespace mmdk {
 
-struct TcState;  // tcgen05 executor state (unet_tc.cu)
+struct TcState;     // per-layer tcgen05 executor state (unet_tc.cu)
+struct FusedState;  // persistent whole-forward tcgen05 executor state (unet_fused.cu)
 
 struct UnetImpl {
   mmdk_unet_config cfg{};
@@ -19,6 +21,9 @@ struct UnetImpl {
   int ffma_S = 1;               // samples per CTA of the fp32 executor
   int attn_scratch_floats = 0;  // shared scratch of the LinearAttention op (qkv + context + stats), 0 without attention
   TcState* tc = nullptr;
+  std::map<int, FusedState*> fused;   // per batch size (bounded; see unet_forward_fused)
+  FusedState* fused_last = nullptr;
+  int last_mode = 0;
 };
 
 int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names, const float* const* tensors,
@@ -26,7 +31,12 @@ int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* n
 void unet_destroy(UnetImpl* net);
 int unet_forward_ffma(const UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream);
 
-// tcgen05 executor (unet_tc.cu)
+// persistent whole-forward tcgen05 executor (unet_fused.cu)
+int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream);
+void unet_fused_release(UnetImpl* net);
+int unet_fused_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out, cudaStream_t stream);
+
+// per-layer tcgen05 executor (unet_tc.cu)
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream);
 void unet_tc_release(UnetImpl* net);
 int unet_tc_timeline(UnetImpl* net, int op_index, long long* dbg_dev, cudaStream_t stream);

@@ -1,0 +1,824 @@
+// Persistent whole-forward tcgen05 executor of the TemporalUnet: ONE launch per forward.
+//
+// Reference semantics: mmd/models/layers/layers.py:261-358, temporal_unet.py:121-174 (the same Op program and the same
+// "tile image" activation format as unet_tc.cu, which runs one launch per layer and is kept as the A/B baseline).
+//
+// Why: the per-layer executor (round 1) serialises load -> MMA -> epilogue inside a CTA (tensor pipe idle ~45% of a CTA's
+// lifetime) and pays 34 launches per forward.  Here every CTA owns up to two tiles (2 x 7 samples) at a time and walks
+// the whole layer program tile-major:
+//     item = (tile parity, op);  items alternate between the two tiles
+// so the tensor pipe works on tile Y's op j while the 16 epilogue warps finish tile X's op j (and vice versa): a two-stage
+// software pipeline with in-order queues between four warp roles.  Layer-to-layer dependencies are tile-local, so no
+// grid-wide synchronisation exists: the epilogue stores an op's output image to global memory (it stays in the 126 MB
+// L2), fences it for the async proxy and arrives on an mbarrier; the input producer then bulk-copies (TMA, UBLKCP) it
+// back as the next op's A operand.
+//
+//   warps 0-15  epilogue: thread = (TMEM lane = image row, quarter of the columns); the 32 (or 16) accumulator values of
+//               a thread are read ONCE into registers (TMEM is released immediately), GroupNorm statistics via per-row
+//               (sum, M2) partials in shared memory + an 8-thread-per-(sample, group) Chan combination, then
+//               normalise -> Mish -> +cond -> +residual -> FP16 hi/lo split -> 16-byte stores
+//   warp 16     tcgen05.mma issuer (one thread), accumulators double-buffered in TMEM (2 x 256 columns)
+//   warp 17     weight producer: streams every op's packed weight chunks through a 3-stage ring, continuously across ops
+//   warp 18     input producer: bulk-copies the input image(s) of the next item into one of two shared-memory buffers
+//
+// The residual 1x1 convolution of a ResidualTemporalBlock (layers.py:353-356) is evaluated by the block's FIRST conv
+// op (same input x) into a second accumulator region and stored as its own image r; the second conv op then adds r in
+// its epilogue like an identity residual, so no op ever needs more than one input image set in shared memory.
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace mmdk {
+
+namespace {
+
+constexpr int FE_WARPS = 16;
+constexpr int F_WARP_MMA = 16, F_WARP_W = 17, F_WARP_IN = 18;
+constexpr int F_THREADS = 19 * 32;
+constexpr int F_STAGES = 3;
+constexpr uint32_t F_STAGE_BYTES = 16384;
+constexpr int F_PART_ROWS = 512;
+constexpr int F_MAX_N = 128;
+
+// epilogue variants of the conv block: (m-tiles per image, columns per m-tile)
+enum FVariant : int { FV_4_32 = 0, FV_2_64 = 1, FV_1_128 = 2, FV_2_32 = 3, FV_1_64 = 4, FV_GENERIC = 5 };
+
+struct FOp {
+  int kind, L, P, n_mt, N, cout, variant;
+  int n_src;
+  const uint8_t* src[MAX_SRC];
+  uint32_t src_tile_bytes[MAX_SRC];
+  uint32_t src_smem_off[MAX_SRC];
+  int src_by_tile[MAX_SRC];   // 1: image indexed by tile (the packed network input), 0: by the CTA's slot
+  uint32_t in_bytes;
+  int big;                    // inputs need both buffers
+  const uint8_t* wchunks;
+  int chunk_base, n_chunks;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* res_bias;      // bias of the residual 1x1 conv evaluated by this op into region 1 (-> out2), or nullptr
+  int cond_off;               // offset into the cond row of the timestep, or -1
+  const uint8_t* res_id;      // image added in the epilogue (identity residual x, or the r image), or nullptr
+  uint32_t res_id_tile_bytes;
+  int res_id_rows, res_id_C;
+  uint8_t* out;
+  uint32_t out_tile_bytes;
+  int out_L, out_rows, out_C;
+  uint8_t* out2;
+  uint32_t out2_tile_bytes;
+  int out2_rows, out2_C;
+};
+
+struct FParams {
+  const FOp* ops;
+  const ChunkDesc* chunks;
+  int n_ops, n_tiles, B;
+  int by_slot;                // 1: intermediate images are indexed by (CTA, parity) slot (L2-resident footprint), 0: by tile
+  const float* cond_row;
+  float* eps;
+  uint32_t buf_bytes;
+  uint32_t off_ring, off_prm, off_part, off_stat, off_bar;
+};
+
+// barrier slots
+constexpr int B_IN_FULL = 0, B_IN_EMPTY = 2, B_ACC_FULL = 4, B_ACC_EMPTY = 6, B_OUT_DONE = 8, B_W_FULL = 10,
+              B_W_EMPTY = 10 + F_STAGES, B_COUNT = 10 + 2 * F_STAGES;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int NH>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+  if constexpr (NH == 32) tmem_ld32(taddr, v);
+  else if constexpr (NH == 16) tmem_ld16(taddr, v);
+  else tmem_ld8(taddr, v);
+}
+
+__device__ __forceinline__ uint4 ld_cg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
+struct EpiCtx {
+  int tid, warp, lane, q4, cb, row;
+  float4* prm4;      // [N] (bias, gamma, beta, cond) of this item
+  float* prm_rb;     // [N] residual-conv bias
+  float2* part;      // [8][F_PART_ROWS] (sum, M2) per group and image row
+  float2* stat;      // [ST * 8] (mean, rstd) of this item
+  uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
+  int tile, img, B;
+};
+
+// Conv1dBlock epilogue (+cond, +residual image), NMT m-tiles of N columns.
+template <int NMT, int N>
+__device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const EpiCtx& c, uint32_t bar_acc_empty) {
+  constexpr int NH = N / 4;          // columns per thread and m-tile
+  constexpr int CPG = N / 8;         // channels per GroupNorm group
+  constexpr int NP = NH / 8;         // 8-channel panels per thread and m-tile
+  static_assert(NH == 2 * CPG, "a thread covers exactly two groups");
+  const int L = op->L, Pp = op->P;
+  const int c0 = c.cb * NH;
+  const uint32_t lane_base = c.tmem + ((uint32_t)(c.q4 * 32) << 16);
+  const uint32_t pinv = (65536u + (uint32_t)Pp - 1u) / (uint32_t)Pp;   // q / Pp for q < 512, Pp >= 10
+
+  // ---- residual 1x1 conv evaluated by this op (region 1): r = acc1 + bias -> image out2 -------------------------
+  if (op->out2 != nullptr) {
+    const size_t oplane = (size_t)(op->out2_C / 8) * op->out2_rows * 16;
+#pragma unroll 1
+    for (int i = 0; i < NMT; ++i) {
+      const int q = 128 * i + c.row;
+      const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
+      const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+      uint8_t* obase = op->out2 + (size_t)c.img * op->out2_tile_bytes + (size_t)(2 + q) * 16;
+#pragma unroll 1
+      for (int pc = 0; pc < NP; ++pc) {
+        float y[8];
+        tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, y);
+        tmem_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] += c.prm_rb[c0 + pc * 8 + e];
+          uint4 hi, lo;
+          split8(y, hi, lo);
+          uint8_t* ob = obase + (size_t)((c0 >> 3) + pc) * op->out2_rows * 16;
+          *reinterpret_cast<uint4*>(ob) = hi;
+          *reinterpret_cast<uint4*>(ob + oplane) = lo;
+        }
+      }
+    }
+  }
+  // ---- accumulators -> registers, TMEM released ---------------------------------------------------------------------
+  float v[NMT][NH];
+#pragma unroll
+  for (int i = 0; i < NMT; ++i) tmem_ldn<NH>(lane_base + i * N + c0, v[i]);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(bar_acc_empty);
+
+  // ---- + bias, per-row (sum, M2) of both groups ----------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < NMT; ++i) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float sm = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPG; ++k) {
+        const float t = v[i][g * CPG + k] + c.prm4[c0 + g * CPG + k].x;
+        v[i][g * CPG + k] = t;
+        sm += t;
+      }
+      const float m = sm * (1.f / CPG);
+      float m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPG; ++k) { const float d = v[i][g * CPG + k] - m; m2 = fmaf(d, d, m2); }
+      c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, m2);
+    }
+  }
+  epi_bar16();
+  // ---- Chan combination: 8 threads per (sample, group) ----------------------------------------------------------------
+  if (c.tid < ST * 8 * 8) {
+    const int pair = c.tid >> 3, sub = c.tid & 7;
+    const int s = pair >> 3, g = pair & 7;
+    const float2* pg = c.part + g * F_PART_ROWS + s * Pp;
+    const float inv_n = 1.f / (float)(CPG * L);
+    float sum = 0.f;
+    for (int pp = sub; pp < L; pp += 8) sum += pg[pp].x;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * inv_n;
+    float m2 = 0.f;
+    for (int pp = sub; pp < L; pp += 8) {
+      const float2 e = pg[pp];
+      const float d = e.x * (1.f / CPG) - mean;
+      m2 += e.y + (float)CPG * d * d;
+    }
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
+    if (sub == 0) c.stat[pair] = make_float2(mean, rsqrtf(m2 * inv_n + 1e-5f));
+  }
+  epi_bar16();
+  // ---- normalise, Mish, +cond, +residual image, split, store ----------------------------------------------------------
+  const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
+  const size_t rplane = (size_t)(op->res_id_C / 8) * op->res_id_rows * 16;
+#pragma unroll
+  for (int i = 0; i < NMT; ++i) {
+    const int q = 128 * i + c.row;
+    const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
+    const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+    if (ok) {
+      const int r = 2 + q;
+      const float2 st0 = c.stat[si * 8 + c.cb * 2], st1 = c.stat[si * 8 + c.cb * 2 + 1];
+      const uint8_t* rbase = op->res_id ? op->res_id + (size_t)c.img * op->res_id_tile_bytes + (size_t)r * 16 : nullptr;
+      uint8_t* obase = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)r * 16;
+      uint4 rh[NP], rl[NP];
+      if (rbase) {
+#pragma unroll
+        for (int pc = 0; pc < NP; ++pc) {
+          rh[pc] = ld_cg_u4(rbase + (size_t)((c0 >> 3) + pc) * op->res_id_rows * 16);
+          rl[pc] = ld_cg_u4(rbase + (size_t)((c0 >> 3) + pc) * op->res_id_rows * 16 + rplane);
+        }
+      }
+#pragma unroll
+      for (int pc = 0; pc < NP; ++pc) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = pc * 8 + e;
+          const float2 st = (k < CPG) ? st0 : st1;
+          const float4 pr = c.prm4[c0 + k];
+          float t = (v[i][k] - st.x) * st.y;
+          t = fmaf(t, pr.y, pr.z);
+          y[e] = mish_fast(t) + pr.w;
+        }
+        if (rbase) add8(rh[pc], rl[pc], y);
+        uint4 hi, lo;
+        split8(y, hi, lo);
+        uint8_t* ob = obase + (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
+        *reinterpret_cast<uint4*>(ob) = hi;
+        *reinterpret_cast<uint4*>(ob + oplane) = lo;
+      }
+    }
+  }
+}
+
+// Down / up resampling convs and the final 1x1 conv: bias only, no normalisation (layers.py:261-276, temporal_unet.py:116-119)
+__device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiCtx& c, uint32_t bar_acc_empty, float* eps) {
+  const int N = op->N, NMT = op->n_mt, L = op->L, Pp = op->P;
+  const uint32_t lane_base = c.tmem + ((uint32_t)(c.q4 * 32) << 16);
+  const uint32_t pinv = (65536u + (uint32_t)Pp - 1u) / (uint32_t)Pp;
+  if (op->kind == TC_FINAL) {
+    if (c.cb == 0) {
+#pragma unroll 1
+      for (int i = 0; i < NMT; ++i) {
+        const int q = 128 * i + c.row;
+        const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
+        const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+        float y[8];
+        tmem_ld8(lane_base + i * N, y);
+        tmem_wait_ld();
+        if (ok) {
+          const size_t b = (size_t)c.tile * ST + si;
+          *reinterpret_cast<float4*>(eps + (b * L + pi) * 4) =
+              make_float4(y[0] + c.prm4[0].x, y[1] + c.prm4[1].x, y[2] + c.prm4[2].x, y[3] + c.prm4[3].x);
+        }
+      }
+    }
+  } else {
+    const int NH = N / 4, c0 = c.cb * NH;
+    const int Po = op->out_L + 2;
+    const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
+    const int n_regions = (op->kind == TC_UP) ? 2 : 1;
+#pragma unroll 1
+    for (int region = 0; region < n_regions; ++region) {
+#pragma unroll 1
+      for (int i = 0; i < NMT; ++i) {
+        const int q = 128 * i + c.row;
+        const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
+        bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+        int ro;
+        if (op->kind == TC_DOWN) {   // stride-2 conv evaluated at every position; keep the even ones
+          ok = ok && ((pi & 1) == 0);
+          ro = 2 + si * Po + (pi >> 1);
+        } else {                      // transposed conv: region 0 -> output 2p, region 1 -> 2p + 1
+          ro = 2 + si * Po + 2 * pi + region;
+        }
+        uint8_t* obase = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)ro * 16;
+#pragma unroll 1
+        for (int pc = 0; pc < NH / 8; ++pc) {
+          const int cbase = c0 + pc * 8;
+          float y[8];
+          tmem_ld8(lane_base + region * 128 + i * N + cbase, y);
+          tmem_wait_ld();
+          if (ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] += c.prm4[cbase + e].x;
+            uint4 hi, lo;
+            split8(y, hi, lo);
+            uint8_t* ob = obase + (size_t)(cbase / 8) * op->out_rows * 16;
+            *reinterpret_cast<uint4*>(ob) = hi;
+            *reinterpret_cast<uint4*>(ob + oplane) = lo;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(bar_acc_empty);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_constant__ FParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar0 = smem_base + P.off_bar;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * B_COUNT);
+#define FBAR(i) (bar0 + 8u * (uint32_t)(i))
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(FBAR(B_IN_FULL + i), 1);
+      mbar_init(FBAR(B_IN_EMPTY + i), 1);
+      mbar_init(FBAR(B_ACC_FULL + i), 1);
+      mbar_init(FBAR(B_ACC_EMPTY + i), FE_WARPS);
+      mbar_init(FBAR(B_OUT_DONE + i), FE_WARPS);
+    }
+    for (int s = 0; s < F_STAGES; ++s) { mbar_init(FBAR(B_W_FULL + s), 1); mbar_init(FBAR(B_W_EMPTY + s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == F_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                 "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int G = (int)gridDim.x;
+  const int n_my = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+  const int n_rounds = (n_my + 1) / 2;
+  // every role walks the same item sequence: for round: for op: for parity (if that tile exists)
+#define F_FOR_ITEMS                                        \
+  for (int r_ = 0; r_ < n_rounds; ++r_)                    \
+    for (int j = 0; j < P.n_ops; ++j)                      \
+      for (int par = 0; par < 2; ++par)                    \
+        if (2 * r_ + par < n_my)
+
+  if (warp == F_WARP_IN) {
+    // ================= input producer =================
+    if (lane == 0) {
+      int uses0 = 0, uses1 = 0, cpar0 = 0, cpar1 = 0, k = 0;
+      F_FOR_ITEMS {
+        const FOp* op = P.ops + j;
+        const int tile = (int)blockIdx.x + (2 * r_ + par) * G;
+        const int slot = P.by_slot ? (int)blockIdx.x * 2 + par : tile;
+        const int p = k & 1;
+        // the previous item of this tile parity must have stored its output (also keeps the barrier phases in step)
+        const int cpar = par ? cpar1 : cpar0;
+        if (cpar > 0) mbar_wait(FBAR(B_OUT_DONE + par), (uint32_t)((cpar - 1) & 1));
+        const int big = op->big;
+        if ((big || p == 0) && uses0 > 0) mbar_wait(FBAR(B_IN_EMPTY + 0), (uint32_t)((uses0 - 1) & 1));
+        if ((big || p == 1) && uses1 > 0) mbar_wait(FBAR(B_IN_EMPTY + 1), (uint32_t)((uses1 - 1) & 1));
+        const uint32_t base = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
+        uint32_t total = 0;
+        const int ns = op->n_src;
+        for (int s = 0; s < ns; ++s) total += op->src_tile_bytes[s];
+        mbar_expect_tx(FBAR(B_IN_FULL + p), total);
+        for (int s = 0; s < ns; ++s) {
+          const uint32_t tb = op->src_tile_bytes[s];
+          const uint8_t* g = op->src[s] + (size_t)(op->src_by_tile[s] ? tile : slot) * tb;
+          uint32_t off = 0;
+          while (off < tb) {
+            const uint32_t n = min(tb - off, 32768u);
+            bulk_g2s(base + op->src_smem_off[s] + off, g + off, n, FBAR(B_IN_FULL + p));
+            off += n;
+          }
+        }
+        if (big || p == 0) uses0++;
+        if (big || p == 1) uses1++;
+        if (par) cpar1++; else cpar0++;
+        k++;
+      }
+    }
+  } else if (warp == F_WARP_W) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      int n = 0;
+      F_FOR_ITEMS {
+        const FOp* op = P.ops + j;
+        const ChunkDesc* cds = P.chunks + op->chunk_base;
+        const int nc = op->n_chunks;
+        for (int ci = 0; ci < nc; ++ci, ++n) {
+          const int st = n % F_STAGES, use = n / F_STAGES;
+          if (use > 0) mbar_wait(FBAR(B_W_EMPTY + st), (uint32_t)((use - 1) & 1));
+          const uint32_t wb = cds[ci].w_bytes;
+          mbar_expect_tx(FBAR(B_W_FULL + st), wb);
+          bulk_g2s(smem_base + P.off_ring + (uint32_t)st * F_STAGE_BYTES, op->wchunks + cds[ci].w_off, wb, FBAR(B_W_FULL + st));
+        }
+      }
+    }
+  } else if (warp == F_WARP_MMA) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int n = 0, k = 0, nuse0 = 0, nuse1 = 0;   // items that used accumulator / in_full parity 0 / 1
+      F_FOR_ITEMS {
+        const FOp* op = P.ops + j;
+        const int p = k & 1;
+        const int N = op->N, NMT = op->n_mt, big = op->big;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t abase = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
+        const uint32_t dbase = tmem_base + (uint32_t)p * 256u;
+        const int nuse = p ? nuse1 : nuse0;
+        if (nuse > 0) mbar_wait(FBAR(B_ACC_EMPTY + p), (uint32_t)((nuse - 1) & 1));
+        mbar_wait(FBAR(B_IN_FULL + p), (uint32_t)(nuse & 1));
+        tc_fence_after();
+        const ChunkDesc* cds = P.chunks + op->chunk_base;
+        const int nc = op->n_chunks;
+        for (int ci = 0; ci < nc; ++ci, ++n) {
+          const ChunkDesc cd = cds[ci];
+          const int st = n % F_STAGES, use = n / F_STAGES;
+          mbar_wait(FBAR(B_W_FULL + st), (uint32_t)(use & 1));
+          tc_fence_after();
+          const uint32_t wbase = smem_base + P.off_ring + (uint32_t)st * F_STAGE_BYTES;
+          const uint32_t b_plane = (uint32_t)cd.k16 * 2u * (uint32_t)N * 16u;
+          for (int i = 0; i < NMT; ++i) {
+            const uint32_t d_tmem = dbase + (uint32_t)cd.acc * 128u + (uint32_t)(i * N);
+            const uint32_t a_row = abase + cd.a_off + (uint32_t)(2 + 128 * i + cd.d) * 16u;
+            for (int kk = 0; kk < cd.k16; ++kk) {
+              const uint32_t a_hi = a_row + (uint32_t)kk * 2u * cd.a_lbo, a_lo = a_hi + cd.a_plane;
+              const uint32_t b_hi = wbase + (uint32_t)kk * 2u * (uint32_t)N * 16u, b_lo = b_hi + b_plane;
+              const uint64_t da_hi = make_desc(a_hi, cd.a_lbo, 128), da_lo = make_desc(a_lo, cd.a_lbo, 128);
+              const uint64_t db_hi = make_desc(b_hi, (uint32_t)N * 16u, 128), db_lo = make_desc(b_lo, (uint32_t)N * 16u, 128);
+              tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (cd.first && kk == 0) ? 0u : 1u);
+              tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+              tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+            }
+          }
+          tc_commit(FBAR(B_W_EMPTY + st));
+        }
+        tc_commit(FBAR(B_ACC_FULL + p));
+        if (big) { tc_commit(FBAR(B_IN_EMPTY + 0)); tc_commit(FBAR(B_IN_EMPTY + 1)); }
+        else tc_commit(FBAR(B_IN_EMPTY + p));
+        if (p) nuse1++; else nuse0++;
+        k++;
+      }
+    }
+  } else {
+    // ================= epilogue: 16 warps =================
+    EpiCtx c;
+    c.tid = tid; c.warp = warp; c.lane = lane; c.q4 = warp & 3; c.cb = warp >> 2; c.row = c.q4 * 32 + lane;
+    c.part = reinterpret_cast<float2*>(smem + P.off_part);
+    c.B = P.B;
+    int k = 0, nuse0 = 0, nuse1 = 0;
+    F_FOR_ITEMS {
+      const FOp* op = P.ops + j;
+      const int p = k & 1;
+      c.tile = (int)blockIdx.x + (2 * r_ + par) * G;
+      c.img = P.by_slot ? (int)blockIdx.x * 2 + par : c.tile;
+      c.prm4 = reinterpret_cast<float4*>(smem + P.off_prm + (uint32_t)p * (F_MAX_N * 20));
+      c.prm_rb = reinterpret_cast<float*>(c.prm4 + F_MAX_N);
+      c.stat = reinterpret_cast<float2*>(smem + P.off_stat + (uint32_t)p * 512);
+      c.tmem = tmem_base + (uint32_t)p * 256u;
+      // per-channel parameters of this op while its MMAs run
+      const int N = op->N;
+      if (tid < N) {
+        const float* cond = (op->cond_off >= 0) ? P.cond_row + op->cond_off : nullptr;
+        c.prm4[tid] = make_float4((tid < op->cout) ? __ldg(op->bias + tid) : 0.f, op->gamma ? __ldg(op->gamma + tid) : 1.f,
+                                  op->beta ? __ldg(op->beta + tid) : 0.f, cond ? __ldg(cond + tid) : 0.f);
+        c.prm_rb[tid] = op->res_bias ? __ldg(op->res_bias + tid) : 0.f;
+      }
+      epi_bar16();
+      mbar_wait(FBAR(B_ACC_FULL + p), (uint32_t)((p ? nuse1 : nuse0) & 1));
+      tc_fence_after();
+      const uint32_t bae = FBAR(B_ACC_EMPTY + p);
+      if (op->kind == TC_CONVBLOCK) {
+        switch (op->variant) {
+          case FV_4_32: epi_convblock<4, 32>(op, c, bae); break;
+          case FV_2_64: epi_convblock<2, 64>(op, c, bae); break;
+          case FV_1_128: epi_convblock<1, 128>(op, c, bae); break;
+          case FV_2_32: epi_convblock<2, 32>(op, c, bae); break;
+          default: epi_convblock<1, 64>(op, c, bae); break;
+        }
+      } else {
+        epi_plain(op, c, bae, P.eps);
+      }
+      // output image visible to the async proxy (the input producer's bulk copies) before the arrival
+      fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(FBAR(B_OUT_DONE + par));
+      if (p) nuse1++; else nuse0++;
+      k++;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == F_WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+#undef FBAR
+#undef F_FOR_ITEMS
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------------------------
+struct FusedState {
+  int B = 0, n_tiles = 0, grid = 0, by_slot = 0;
+  std::vector<TcImage> images;     // [0] = packed network input, [1 + j] = output of op j
+  std::vector<TcImage> images_r;   // [j] = residual-conv image written by op j (dev == nullptr if none)
+  std::vector<uint8_t*> owned;     // distinct device allocations behind the images (buffers may be shared)
+  uint8_t* w_all = nullptr;
+  FOp* ops_dev = nullptr;
+  ChunkDesc* chunks_dev = nullptr;
+  std::vector<FOp> ops;
+  FParams prm{};
+  size_t smem = 0;
+  size_t activation_bytes = 0;
+};
+
+static void fused_free(FusedState* s) {
+  if (!s) return;
+  for (auto* p : s->owned) cudaFree(p);
+  cudaFree(s->w_all);
+  cudaFree(s->ops_dev);
+  cudaFree(s->chunks_dev);
+  delete s;
+}
+
+void unet_fused_release(UnetImpl* net) {
+  if (!net) return;
+  for (auto& kv : net->fused) fused_free(kv.second);
+  net->fused.clear();
+}
+
+static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, FusedState** out) {
+  const auto& cfg = net->cfg;
+  if (cfg.self_attention) return fail(MMDK_EINVAL, "tensor-core executor: LinearAttention not supported");
+  if (cfg.state_dim > 8) return fail(MMDK_EINVAL, "tensor-core executor: state_dim > 8 not supported");
+  int dev = 0, n_sm = 0, max_smem = 0;
+  MMDK_CUDA(cudaGetDevice(&dev));
+  MMDK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  MMDK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  auto* st = new FusedState();
+  st->B = B;
+  st->n_tiles = (B + ST - 1) / ST;
+  st->grid = std::min(st->n_tiles, n_sm);
+  st->by_slot = by_slot;
+  const int n_img = by_slot ? 2 * st->grid : st->n_tiles;   // entries of every intermediate image
+  const int n_ops = (int)net->ops.size();
+  st->images.resize(n_ops + 1);
+  st->images_r.resize(n_ops);
+  st->ops.resize(n_ops);
+  auto fail_free = [&](const std::string& m) { fused_free(st); return fail(MMDK_EINVAL, m); };
+
+  auto make_image = [&](TcImage& im, int C, int L, int entries) -> int {
+    im.C = C; im.L = L; im.rows = level_rows(L);
+    im.tile_bytes = (uint32_t)C * im.rows * 4;
+    const size_t bytes = (size_t)im.tile_bytes * entries;
+    if (cudaMalloc(&im.dev, bytes) != cudaSuccess) return MMDK_ENOMEM;
+    cudaMemsetAsync(im.dev, 0, bytes, stream);   // halo rows / unused samples stay zero for ever
+    st->owned.push_back(im.dev);
+    st->activation_bytes += bytes;
+    return MMDK_OK;
+  };
+  if (make_image(st->images[0], 16, cfg.horizon, st->n_tiles) != MMDK_OK) return fail_free("out of memory (input image)");
+
+  std::vector<ChunkDesc> all_chunks;
+  struct WSrc { const float* W; int cin, ktaps, tap, ci0, CK, cout, N; uint32_t dst_off; };
+  std::vector<WSrc> wsrc;
+  uint32_t w_total = 0;
+  std::vector<uint32_t> op_w_off(n_ops, 0);
+  uint32_t max_in = 0;
+  std::vector<uint32_t> in_bytes(n_ops, 0);
+
+  for (int j = 0; j < n_ops; ++j) {
+    const Op& op = net->ops[j];
+    FOp& p = st->ops[j];
+    p = FOp{};
+    p.kind = op.type == OP_CONVBLOCK ? TC_CONVBLOCK : op.type == OP_DOWN ? TC_DOWN : op.type == OP_UP ? TC_UP : TC_FINAL;
+    p.L = op.lin; p.P = op.lin + 2;
+    const int rows = level_rows(op.lin);
+    p.n_mt = (rows - 4) / 128;
+    p.cout = op.cout;
+    p.N = op.cout < 16 ? 16 : op.cout;
+    if (p.N != 16 && p.N != 32 && p.N != 64 && p.N != 128) return fail_free("tensor-core executor: unsupported channel count");
+    const int NV = p.n_mt * p.N;
+    if (NV > 128 || p.n_mt * 128 > F_PART_ROWS) return fail_free("tensor-core executor: unsupported (rows, channels) combination for this network shape");
+    p.variant = FV_GENERIC;
+    if (p.kind == TC_CONVBLOCK) {
+      if (op.n_groups != 8) return fail_free("tensor-core executor: GroupNorm needs 8 groups");
+      if (p.n_mt == 4 && p.N == 32) p.variant = FV_4_32;
+      else if (p.n_mt == 2 && p.N == 64) p.variant = FV_2_64;
+      else if (p.n_mt == 1 && p.N == 128) p.variant = FV_1_128;
+      else if (p.n_mt == 2 && p.N == 32) p.variant = FV_2_32;
+      else if (p.n_mt == 1 && p.N == 64) p.variant = FV_1_64;
+      else return fail_free("tensor-core executor: unsupported conv block shape");
+    } else if (p.kind != TC_FINAL && p.N < 32) {
+      return fail_free("tensor-core executor: resampling convs need >= 32 channels");
+    }
+    // output image
+    if (p.kind != TC_FINAL) {
+      if (make_image(st->images[j + 1], op.cout, op.lout, n_img) != MMDK_OK) return fail_free("out of memory (activations)");
+      const TcImage& oi = st->images[j + 1];
+      p.out = oi.dev; p.out_tile_bytes = oi.tile_bytes;
+      p.out_L = oi.L; p.out_rows = oi.rows; p.out_C = oi.C;
+    }
+    auto img_of = [&](int prod) { return prod + 1; };   // -1 (network input) -> image 0
+    std::vector<int> main_imgs = {img_of(op.p_src0)};
+    if (op.p_src1 > -2) main_imgs.push_back(img_of(op.p_src1));
+    // residual handling
+    const bool is_cb = (p.kind == TC_CONVBLOCK);
+    const bool res_id_x = is_cb && op.res_src >= 0 && op.res_w < 0;                 // identity residual: add x
+    const bool res_from_r = is_cb && op.res_w >= 0;                                   // r image written by op j-1
+    bool eval_res = false;                                                            // this op evaluates the NEXT op's residual conv
+    if (is_cb && j + 1 < n_ops) {
+      const Op& nx = net->ops[j + 1];
+      eval_res = nx.type == OP_CONVBLOCK && nx.res_w >= 0 && nx.p_src0 == j && nx.p_res == op.p_src0 && nx.p_res1 == op.p_src1 &&
+                 nx.res_cin == op.cin && nx.cout == op.cout;
+    }
+    if (res_from_r) {
+      if (j == 0 || !st->images_r[j - 1].dev) return fail_free("tensor-core executor: residual conv without a producing block");
+      const TcImage& ri = st->images_r[j - 1];
+      p.res_id = ri.dev; p.res_id_tile_bytes = ri.tile_bytes; p.res_id_rows = ri.rows; p.res_id_C = ri.C;
+    } else if (res_id_x) {
+      const TcImage& ri = st->images[img_of(op.p_res)];
+      p.res_id = ri.dev;
+      p.res_id_tile_bytes = ri.tile_bytes;
+      p.res_id_rows = ri.rows; p.res_id_C = ri.C;
+      if (op.p_res < 0) return fail_free("tensor-core executor: identity residual of the network input is not supported");
+    }
+    uint32_t off = 0;
+    auto add_src = [&](int img) -> int {
+      for (int k = 0; k < p.n_src; ++k) if (p.src[k] == st->images[img].dev) return k;
+      if (p.n_src >= MAX_SRC) return -1;
+      int k = p.n_src++;
+      p.src[k] = st->images[img].dev;
+      p.src_by_tile[k] = (img == 0) ? 1 : 0;
+      p.src_tile_bytes[k] = st->images[img].tile_bytes;
+      p.src_smem_off[k] = off;
+      off += (st->images[img].tile_bytes + 127) & ~127u;
+      return k;
+    };
+    std::vector<ChunkDesc> chunks;
+    auto add_chunks = [&](const std::vector<int>& imgs, int cin_total, int w_off_blob, int ktaps, int tap, int d, int acc,
+                          bool first_in_acc) -> bool {
+      int ci = 0;
+      bool first = first_in_acc;
+      for (size_t si = 0; si < imgs.size(); ++si) {
+        const TcImage& im = st->images[imgs[si]];
+        const int slot = add_src(imgs[si]);
+        if (slot < 0) return false;
+        const int c_here = im.C;
+        for (int c0 = 0; c0 < c_here; c0 += 32) {
+          const int CK = std::min(32, c_here - c0);
+          ChunkDesc cd{};
+          cd.a_off = p.src_smem_off[slot] + (uint32_t)(c0 / 8) * im.rows * 16;
+          cd.a_plane = (uint32_t)(im.C / 8) * im.rows * 16;
+          cd.a_lbo = (uint32_t)im.rows * 16;
+          cd.w_bytes = (uint32_t)CK * p.N * 4;
+          cd.w_off = w_total;
+          wsrc.push_back({net->blob + w_off_blob, cin_total, ktaps, tap, ci + c0, CK, op.cout, p.N, w_total});
+          w_total += cd.w_bytes;
+          cd.d = d; cd.acc = acc; cd.first = first ? 1 : 0; cd.k16 = CK / 16;
+          first = false;
+          chunks.push_back(cd);
+        }
+        ci += (imgs[si] == 0) ? cfg.state_dim : c_here;
+      }
+      return true;
+    };
+    bool okc = true;
+    if (p.kind == TC_CONVBLOCK) {
+      for (int tap = 0; tap < 5; ++tap) okc = okc && add_chunks(main_imgs, op.cin, op.w, 5, tap, tap - 2, 0, tap == 0);
+      if (eval_res) {
+        const Op& nx = net->ops[j + 1];
+        okc = okc && add_chunks(main_imgs, nx.res_cin, nx.res_w, 1, 0, 0, 1, true);
+        if (make_image(st->images_r[j], op.cout, op.lout, n_img) != MMDK_OK) return fail_free("out of memory (residual image)");
+        TcImage& ri = st->images_r[j];
+        p.out2 = ri.dev; p.out2_tile_bytes = ri.tile_bytes; p.out2_rows = ri.rows; p.out2_C = ri.C;
+        p.res_bias = net->blob + nx.res_b;
+      }
+    } else if (p.kind == TC_DOWN) {
+      for (int tap = 0; tap < 3; ++tap) okc = okc && add_chunks(main_imgs, op.cin, op.w, 3, tap, tap - 1, 0, tap == 0);
+    } else if (p.kind == TC_UP) {
+      // out[2m] = x[m] w1 + x[m-1] w3 ; out[2m+1] = x[m+1] w0 + x[m] w2   (ConvTranspose1d k4 s2 p1)
+      okc = okc && add_chunks(main_imgs, op.cin, op.w, 4, 1, 0, 0, true);
+      okc = okc && add_chunks(main_imgs, op.cin, op.w, 4, 3, -1, 0, false);
+      okc = okc && add_chunks(main_imgs, op.cin, op.w, 4, 0, 1, 1, true);
+      okc = okc && add_chunks(main_imgs, op.cin, op.w, 4, 2, 0, 1, false);
+    } else {
+      okc = okc && add_chunks(main_imgs, op.cin, op.w, 1, 0, 0, 0, true);
+    }
+    if (!okc) return fail_free("tensor-core executor: too many input images in one op");
+    p.in_bytes = off;
+    in_bytes[j] = off;
+    max_in = std::max(max_in, off);
+    p.chunk_base = (int)all_chunks.size();
+    p.n_chunks = (int)chunks.size();
+    // chunk weight offsets are relative to the op's base
+    op_w_off[j] = chunks.empty() ? w_total : chunks[0].w_off;
+    for (auto& cd : chunks) { cd.w_off -= op_w_off[j]; all_chunks.push_back(cd); }
+    p.bias = net->blob + op.b;
+    p.cond_off = -1;
+    if (p.kind == TC_CONVBLOCK) {
+      p.gamma = net->blob + op.gn_w;
+      p.beta = net->blob + op.gn_b;
+      p.cond_off = op.cond;
+    }
+  }
+  // shared-memory plan
+  const uint32_t scratch = 2u * (F_MAX_N * 20) + 8u * F_PART_ROWS * 8u + 1024u + 8u * B_COUNT + 16u;
+  const uint32_t avail = (uint32_t)max_smem - F_STAGES * F_STAGE_BYTES - scratch - 256u;
+  uint32_t buf = 0;
+  for (int j = 0; j < n_ops; ++j) if (in_bytes[j] * 2 <= avail) buf = std::max(buf, in_bytes[j]);
+  buf = (buf + 127) & ~127u;
+  if (buf == 0 || max_in > 2 * buf) {
+    // the largest input needs both buffers: grow them as far as shared memory allows
+    buf = std::max(buf, ((max_in + 1) / 2 + 127) & ~127u);
+  }
+  if (2 * buf > avail) return fail_free("tensor-core executor: an op's input images do not fit in shared memory");
+  for (int j = 0; j < n_ops; ++j) st->ops[j].big = in_bytes[j] > buf ? 1 : 0;
+  FParams& P = st->prm;
+  P.buf_bytes = buf;
+  P.off_ring = 2 * buf;
+  P.off_prm = P.off_ring + F_STAGES * F_STAGE_BYTES;
+  P.off_part = P.off_prm + 2u * (F_MAX_N * 20);
+  P.off_stat = P.off_part + 8u * F_PART_ROWS * 8u;
+  P.off_bar = P.off_stat + 1024u;
+  st->smem = P.off_bar + 8u * B_COUNT + 16u;
+  if (st->smem > (size_t)max_smem) return fail_free("tensor-core executor: shared-memory plan exceeds the device limit");
+
+  // weights
+  if (cudaMalloc(&st->w_all, std::max<uint32_t>(w_total, 16)) != cudaSuccess) return fail_free("out of memory (packed weights)");
+  for (const auto& w : wsrc)
+    pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, w.cout, w.tap, w.ci0, w.CK, w.N,
+                                              reinterpret_cast<__half*>(st->w_all + w.dst_off));
+  for (int j = 0; j < n_ops; ++j) st->ops[j].wchunks = st->w_all + op_w_off[j];
+  if (cudaMalloc(&st->ops_dev, sizeof(FOp) * n_ops) != cudaSuccess ||
+      cudaMalloc(&st->chunks_dev, sizeof(ChunkDesc) * std::max<size_t>(all_chunks.size(), 1)) != cudaSuccess)
+    return fail_free("out of memory (op table)");
+  cudaMemcpyAsync(st->ops_dev, st->ops.data(), sizeof(FOp) * n_ops, cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(st->chunks_dev, all_chunks.data(), sizeof(ChunkDesc) * all_chunks.size(), cudaMemcpyHostToDevice, stream);
+  // the host vectors must outlive the async copies
+  if (check_cuda(cudaStreamSynchronize(stream), "tensor-core executor setup") != MMDK_OK) { fused_free(st); return MMDK_ECUDA; }
+  P.ops = st->ops_dev;
+  P.chunks = st->chunks_dev;
+  P.n_ops = n_ops;
+  P.n_tiles = st->n_tiles;
+  P.B = B;
+  P.by_slot = by_slot;
+  *out = st;
+  return MMDK_OK;
+}
+
+int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream) {
+  FusedState* st = nullptr;
+  auto it = net->fused.find(B);
+  if (it != net->fused.end()) st = it->second;
+  if (!st) {
+    // bounded cache of per-batch-size states (planner warm-up at B=2, sampling at B=K, batched sampling at B=R*K)
+    if (net->fused.size() >= 4) {
+      auto victim = net->fused.begin();
+      for (auto i2 = net->fused.begin(); i2 != net->fused.end(); ++i2)
+        if (i2->second->activation_bytes > victim->second->activation_bytes) victim = i2;
+      fused_free(victim->second);
+      net->fused.erase(victim);
+    }
+    int rc = build_fused(net, B, 0, stream, &st);
+    if (rc != MMDK_OK) return rc;
+    net->fused[B] = st;
+  }
+  net->fused_last = st;
+  {
+    int dev = 0;
+    MMDK_CUDA(cudaGetDevice(&dev));
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64) return fail(MMDK_EINVAL, "device index out of range");
+    if (!configured[dev]) {
+      int max_optin = 0;
+      MMDK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      MMDK_CUDA(cudaFuncSetAttribute(unet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+      configured[dev] = true;
+    }
+  }
+  const auto& cfg = net->cfg;
+  {
+    const TcImage& im = st->images[0];
+    const int n = B * cfg.horizon;
+    pack_input_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, B, cfg.horizon, cfg.state_dim, im.rows, im.dev, im.tile_bytes);
+  }
+  FParams P = st->prm;
+  P.cond_row = net->cond_table + (size_t)t * net->n_cond;
+  P.eps = eps;
+  unet_fused_kernel<<<st->grid, F_THREADS, st->smem, stream>>>(P);
+  return check_cuda(cudaGetLastError(), "unet_fused_kernel launch");
+}
+
+int unet_fused_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out, cudaStream_t stream) {
+  FusedState* st = net->fused_last;
+  if (!st) return fail(MMDK_EINVAL, "run a tensor-core forward first");
+  if (op_index < -1 || op_index + 1 >= (int)st->images.size() || !st->images[op_index + 1].dev)
+    return fail(MMDK_EINVAL, "op index out of range (or op has no activation image)");
+  if (st->by_slot) return fail(MMDK_EINVAL, "activation taps need the per-tile image mode");
+  const TcImage& im = st->images[op_index + 1];
+  if (c_out) *c_out = im.C;
+  if (l_out) *l_out = im.L;
+  if (!out) return MMDK_OK;
+  const int n = st->B * im.C * im.L;
+  unpack_image_kernel<<<(n + 255) / 256, 256, 0, stream>>>(im.dev, im.tile_bytes, st->B, im.C, im.L, im.rows, out);
+  return check_cuda(cudaGetLastError(), "unpack_image_kernel");
+}
+
+}  // namespace mmdk

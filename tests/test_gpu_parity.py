@@ -479,7 +479,7 @@ def test_peer_table_sizes_cross_smem_boundary(pair, dev, n_peers):
     o, p = pair
     R, K = 2, 128
     g = torch.Generator().manual_seed(n_peers)
-    x = torch.randn(R * K, 64, 4, generator=g) * 0.3
+    x = (torch.randn(R * K, 64, 4, generator=g) * 0.3).clamp(-0.95, 0.95)
     xd = x.to(dev)
     peers_h = torch.rand(n_peers, 64, 2, generator=g) * 1.2 - 0.6
     peers_h[5] = torch.rand(64, 2, generator=g) * 3.0 - 1.5   # one robot wandering outside the hash box (clamped cells)
