@@ -88,13 +88,16 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
                         void* stream);
 
 /* Debug: from the next MMDK_UNET_F16X3 forward on, op `op_index` writes a per-CTA clock64 timeline into
- * dbg_dev [n_tiles, 16] int64 (slot 15 = SM id); op_index = -1 / dbg_dev = NULL switches it off. */
+ * dbg_dev [n_tiles, 16] int64 (slot 15 = SM id); op_index = -1 / dbg_dev = NULL switches it off (per-layer executor).
+ * op_index = -2: the persistent executor (MMDK_UNET_F16X3) writes CTA 0's per-item stamps [n_items, 16] int64 into dbg_dev
+ * (0 load issued, 1 input in shared memory, 2 MMAs issued, 3 accumulators complete, 5 output stored, 6 cycles the
+ * issuer waited for weights, 7 epilogue idle since); dbg_dev = NULL switches it off. */
 int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream);
 
-/* Calibration (profiles/): n_ctas CTAs each issue n_iters back-to-back tcgen05.mma (M=128, N, K=16, kind::f16) and
- * write {elapsed clock64 cycles, n_iters} to out_dev [n_ctas, 2] int64.  Run under ncu to read what
- * sm__pipe_tensor_cycles_active reports for a loop that is 100% MMA issue. */
-int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, void* stream);
+/* Calibration (profiles/): n_ctas CTAs each issue n_iters back-to-back tcgen05.mma (M=128, N, K=16, kind::f16, SS mode)
+ * rotating over n_acc (1, 2 or 4) TMEM accumulators, and write {elapsed clock64 cycles, n_iters} to out_dev
+ * [n_ctas, 2] int64.  Run under ncu to read what sm__pipe_tensor_cycles_active reports for a loop that is 100% MMA. */
+int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, int n_acc, long long* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Guide + DDPM step  (mmd/models/diffusion_models/guides.py:152-253, sample_functions.py:41-107,

@@ -83,7 +83,7 @@ def load():
     lib.mmdk_unet_cond_row.argtypes = [vp, i, vp, c_int_p, vp]
     lib.mmdk_unet_debug_tap.argtypes = [vp, i, vp, c_int_p, c_int_p, c_int_p, vp]
     lib.mmdk_unet_debug_timeline.argtypes = [vp, i, vp, vp]
-    lib.mmdk_debug_mma_calibrate.argtypes = [i, i, i, vp, vp]
+    lib.mmdk_debug_mma_calibrate.argtypes = [i, i, i, i, vp, vp]
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]

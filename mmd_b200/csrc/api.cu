@@ -96,12 +96,13 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
 
 int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream) {
   if (!net) return fail(MMDK_EINVAL, "null argument");
+  if (op_index == -2) { net->impl->fused_dbg = dbg_dev; return MMDK_OK; }   // fused executor: per-item timeline of CTA 0
   return unet_tc_timeline(net->impl, op_index, dbg_dev, (cudaStream_t)stream);
 }
 
-int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, void* stream) {
+int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, int n_acc, long long* out_dev, void* stream) {
   if (!out_dev) return fail(MMDK_EINVAL, "null argument");
-  return mma_calibrate(N, n_iters, n_ctas, out_dev, (cudaStream_t)stream);
+  return mma_calibrate(N, n_iters, n_ctas, n_acc, out_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

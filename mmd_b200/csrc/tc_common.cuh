@@ -77,10 +77,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: park, do not spin
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {   // long waits: do not hog issue slots
   uint32_t done = 0;
@@ -163,11 +163,33 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with the 64-bit shared-memory descriptors given as (low word, shared high word): K-major, no swizzle,
+// SBO = 128 B and descriptor version 1 live in the high word (0x4008), start address >> 4 and LBO >> 4 in the low word,
+// so walking taps / m-tiles / K steps / hi-lo planes is one 32-bit add on the low word.  Executed by the whole (converged)
+// warp with uniform operands; only the elected lane issues.
+constexpr uint32_t F_DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ void mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(leader), "r"(F_DESC_HI) : "memory");
+}
+
 __device__ __forceinline__ float mish_fast(float y) {
-  float e = __expf(y);
+  // y * tanh(softplus(y)) = y * n / (n + 2), n = e^y (e^y + 2); for y >= 20 the ratio is exactly 1 in fp32, so clamping
+  // the exponent's argument replaces the overflow guard
+  float e = __expf(fminf(y, 20.f));
   float n = e * (e + 2.f);
-  float m = y * __fdividef(n, n + 2.f);
-  return (y > 20.f) ? y : m;
+  return y * __fdividef(n, n + 2.f);
 }
 
 // 8 fp32 -> 8 fp16 hi (uint4) + 8 fp16 lo (uint4)

@@ -24,6 +24,7 @@ struct UnetImpl {
   std::map<int, FusedState*> fused;   // per batch size (bounded; see unet_forward_fused)
   FusedState* fused_last = nullptr;
   int last_mode = 0;
+  long long* fused_dbg = nullptr;   // debug timeline buffer of the fused executor (mmdk_unet_debug_timeline)
 };
 
 int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names, const float* const* tensors,
@@ -40,7 +41,7 @@ int unet_fused_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_o
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream);
 void unet_tc_release(UnetImpl* net);
 int unet_tc_timeline(UnetImpl* net, int op_index, long long* dbg_dev, cudaStream_t stream);
-int mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, cudaStream_t stream);
+int mma_calibrate(int N, int n_iters, int n_ctas, int n_acc, long long* out_dev, cudaStream_t stream);
 int unet_tc_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out, cudaStream_t stream);
 
 }  // namespace mmdk

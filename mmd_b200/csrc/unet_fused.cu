@@ -25,6 +25,7 @@
 // op (same input x) into a second accumulator region and stored as its own image r; the second conv op then adds r in
 // its epilogue like an identity residual, so no op ever needs more than one input image set in shared memory.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -52,6 +53,8 @@ struct FOp {
   const uint8_t* src[MAX_SRC];
   uint32_t src_tile_bytes[MAX_SRC];
   uint32_t src_smem_off[MAX_SRC];
+  uint32_t src_lbo[MAX_SRC];    // bytes between K panels of the source image (rows * 16)
+  uint32_t src_plane[MAX_SRC];  // bytes from its hi plane to its lo plane
   int src_by_tile[MAX_SRC];   // 1: image indexed by tile (the packed network input), 0: by the CTA's slot
   uint32_t in_bytes;
   int big;                    // inputs need both buffers
@@ -73,15 +76,31 @@ struct FOp {
   int out2_rows, out2_C;
 };
 
+// weight chunk, 16 bytes (one uniform constant load per chunk); everything the MMA issuer needs is precomputed on the host
+struct __align__(16) FChunk {
+  uint32_t a_w;      // low word of the A descriptor at (m-tile 0, K step 0, hi plane), RELATIVE to the item's input buffer:
+                     // ((a_off + (2 + tap shift) * 16) >> 4) | (LBO >> 4) << 16; the issuer adds (buffer base >> 4)
+  uint32_t a_ks_pl;  // (bytes per K step of A) >> 4  |  ((hi -> lo plane distance) >> 4) << 16
+  uint32_t w_off;    // byte offset of the packed weights relative to the op's wchunks
+  uint32_t meta;     // acc | first << 1 | k16 << 2
+};
+constexpr int F_MAX_OPS = 40, F_MAX_CHUNKS = 448;
+
+// The op and chunk tables live in the kernel PARAMETER bank (16 KB of the 32 KB CUDA 12 allows): indexed by warp-uniform
+// loop counters they are read with uniform constant loads, so the MMA issuer's descriptor arithmetic stays in uniform
+// registers (round-2 timeline: with the tables in global memory the issue loop, not the tensor pipe, set the pace:
+// ~120 cycles per tcgen05.mma).
 struct FParams {
-  const FOp* ops;
-  const ChunkDesc* chunks;
   int n_ops, n_tiles, B;
   int by_slot;                // 1: intermediate images are indexed by (CTA, parity) slot (L2-resident footprint), 0: by tile
   const float* cond_row;
   float* eps;
   uint32_t buf_bytes;
   uint32_t off_ring, off_prm, off_part, off_stat, off_bar;
+  int dbg_flags;              // timing experiments only (MMDK_FUSED_DEBUG): 1 = no weight copies after the first ring fill, 2 = hi*hi term only
+  long long* dbg;             // optional timeline of CTA 0: [item][16] clock64 stamps (see tests/tc_timeline.py), nullptr in production
+  FOp ops[F_MAX_OPS];
+  FChunk chunks[F_MAX_CHUNKS];
 };
 
 // barrier slots
@@ -91,7 +110,7 @@ constexpr int B_IN_FULL = 0, B_IN_EMPTY = 2, B_ACC_FULL = 4, B_ACC_EMPTY = 6, B_
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <int NH>
@@ -111,6 +130,7 @@ struct EpiCtx {
   float2* stat;      // [ST * 8] (mean, rstd) of this item
   uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
   int tile, img, B;
+  long long* dbg;    // this item's stamp row (CTA 0, thread 0 only) or nullptr
 };
 
 // Conv1dBlock epilogue (+cond, +residual image), NMT m-tiles of N columns.
@@ -159,6 +179,26 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(bar_acc_empty);
+  if (c.dbg) c.dbg[8] = clock64();
+
+  // rows of this thread (one per m-tile) and the first residual panel: its L2-latency load overlaps the statistics
+  const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
+  const size_t rplane = (size_t)(op->res_id_C / 8) * op->res_id_rows * 16;
+  const uint8_t* rimg = op->res_id ? op->res_id + (size_t)c.img * op->res_id_tile_bytes + (size_t)(c0 >> 3) * op->res_id_rows * 16 : nullptr;
+  bool okv[NMT];
+  int siv[NMT];
+#pragma unroll
+  for (int i = 0; i < NMT; ++i) {
+    const int q = 128 * i + c.row;
+    siv[i] = (int)(((uint32_t)q * pinv) >> 16);
+    const int pi = q - siv[i] * Pp;
+    okv[i] = (siv[i] < ST) && (pi < L) && (c.tile * ST + siv[i] < c.B);
+  }
+  uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
+  if (rimg && okv[0]) {
+    rh = ld_cg_u4(rimg + (size_t)(2 + c.row) * 16);
+    rl = ld_cg_u4(rimg + (size_t)(2 + c.row) * 16 + rplane);
+  }
 
   // ---- + bias, per-row (sum, M2) of both groups ----------------------------------------------------------------------
 #pragma unroll
@@ -179,7 +219,9 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
       c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, m2);
     }
   }
+  if (c.dbg) c.dbg[9] = clock64();
   epi_bar16();
+  if (c.dbg) c.dbg[10] = clock64();
   // ---- Chan combination: 8 threads per (sample, group) ----------------------------------------------------------------
   if (c.tid < ST * 8 * 8) {
     const int pair = c.tid >> 3, sub = c.tid & 7;
@@ -204,48 +246,44 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     if (sub == 0) c.stat[pair] = make_float2(mean, rsqrtf(m2 * inv_n + 1e-5f));
   }
   epi_bar16();
-  // ---- normalise, Mish, +cond, +residual image, split, store ----------------------------------------------------------
-  const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
-  const size_t rplane = (size_t)(op->res_id_C / 8) * op->res_id_rows * 16;
+  if (c.dbg) c.dbg[11] = clock64();
+  // ---- normalise, Mish, +cond, +residual image, split, store: one flat sequence of (m-tile, panel) steps with the
+  // residual of the NEXT step already in flight ------------------------------------------------------------------------
 #pragma unroll
-  for (int i = 0; i < NMT; ++i) {
-    const int q = 128 * i + c.row;
-    const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
-    const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
-    if (ok) {
-      const int r = 2 + q;
-      const float2 st0 = c.stat[si * 8 + c.cb * 2], st1 = c.stat[si * 8 + c.cb * 2 + 1];
-      const uint8_t* rbase = op->res_id ? op->res_id + (size_t)c.img * op->res_id_tile_bytes + (size_t)r * 16 : nullptr;
-      uint8_t* obase = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)r * 16;
-      uint4 rh[NP], rl[NP];
-      if (rbase) {
-#pragma unroll
-        for (int pc = 0; pc < NP; ++pc) {
-          rh[pc] = ld_cg_u4(rbase + (size_t)((c0 >> 3) + pc) * op->res_id_rows * 16);
-          rl[pc] = ld_cg_u4(rbase + (size_t)((c0 >> 3) + pc) * op->res_id_rows * 16 + rplane);
-        }
-      }
-#pragma unroll
-      for (int pc = 0; pc < NP; ++pc) {
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = pc * 8 + e;
-          const float2 st = (k < CPG) ? st0 : st1;
-          const float4 pr = c.prm4[c0 + k];
-          float t = (v[i][k] - st.x) * st.y;
-          t = fmaf(t, pr.y, pr.z);
-          y[e] = mish_fast(t) + pr.w;
-        }
-        if (rbase) add8(rh[pc], rl[pc], y);
-        uint4 hi, lo;
-        split8(y, hi, lo);
-        uint8_t* ob = obase + (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
-        *reinterpret_cast<uint4*>(ob) = hi;
-        *reinterpret_cast<uint4*>(ob + oplane) = lo;
+  for (int step = 0; step < NMT * NP; ++step) {
+    const int i = step / NP, pc = step % NP;
+    const uint4 ch = rh, cl = rl;
+    if (step + 1 < NMT * NP) {
+      const int i2 = (step + 1) / NP, pc2 = (step + 1) % NP;
+      if (rimg && okv[i2]) {
+        const uint8_t* rp = rimg + (size_t)(2 + 128 * i2 + c.row) * 16 + (size_t)pc2 * op->res_id_rows * 16;
+        rh = ld_cg_u4(rp);
+        rl = ld_cg_u4(rp + rplane);
       }
     }
+    if (okv[i]) {
+      const int si = siv[i];
+      const float2 st0 = c.stat[si * 8 + c.cb * 2], st1 = c.stat[si * 8 + c.cb * 2 + 1];
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = pc * 8 + e;
+        const float2 st = (k < CPG) ? st0 : st1;
+        const float4 pr = c.prm4[c0 + k];
+        float t = (v[i][k] - st.x) * st.y;
+        t = fmaf(t, pr.y, pr.z);
+        y[e] = mish_fast(t) + pr.w;
+      }
+      if (rimg) add8(ch, cl, y);
+      uint4 hi, lo;
+      split8(y, hi, lo);
+      uint8_t* ob = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)(2 + 128 * i + c.row) * 16 +
+                    (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
+      *reinterpret_cast<uint4*>(ob) = hi;
+      *reinterpret_cast<uint4*>(ob + oplane) = lo;
+    }
   }
+  if (c.dbg) c.dbg[12] = clock64();
 }
 
 // Down / up resampling convs and the final 1x1 conv: bias only, no normalisation (layers.py:261-276, temporal_unet.py:116-119)
@@ -321,6 +359,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
   const uint32_t bar0 = smem_base + P.off_bar;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 8 * B_COUNT);
 #define FBAR(i) (bar0 + 8u * (uint32_t)(i))
+#define FSTAMP(item, slot) do { if (P.dbg && blockIdx.x == 0) P.dbg[(size_t)(item) * 16 + (slot)] = clock64(); } while (0)
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -358,7 +397,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
     if (lane == 0) {
       int uses0 = 0, uses1 = 0, cpar0 = 0, cpar1 = 0, k = 0;
       F_FOR_ITEMS {
-        const FOp* op = P.ops + j;
+        const FOp* op = &P.ops[j];
         const int tile = (int)blockIdx.x + (2 * r_ + par) * G;
         const int slot = P.by_slot ? (int)blockIdx.x * 2 + par : tile;
         const int p = k & 1;
@@ -368,6 +407,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
         const int big = op->big;
         if ((big || p == 0) && uses0 > 0) mbar_wait(FBAR(B_IN_EMPTY + 0), (uint32_t)((uses0 - 1) & 1));
         if ((big || p == 1) && uses1 > 0) mbar_wait(FBAR(B_IN_EMPTY + 1), (uint32_t)((uses1 - 1) & 1));
+        FSTAMP(k, 0);
         const uint32_t base = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
         uint32_t total = 0;
         const int ns = op->n_src;
@@ -392,62 +432,105 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
   } else if (warp == F_WARP_W) {
     // ================= weight producer =================
     if (lane == 0) {
-      int n = 0;
+      int st = 0, use = 0;
       F_FOR_ITEMS {
-        const FOp* op = P.ops + j;
-        const ChunkDesc* cds = P.chunks + op->chunk_base;
-        const int nc = op->n_chunks;
-        for (int ci = 0; ci < nc; ++ci, ++n) {
-          const int st = n % F_STAGES, use = n / F_STAGES;
+        const FOp* op = &P.ops[j];
+        const int nc = op->n_chunks, cb0 = op->chunk_base;
+        const uint32_t Nw = (uint32_t)op->N;
+        for (int ci = 0; ci < nc; ++ci, st = (st + 1 == F_STAGES) ? 0 : st + 1, use += (st == 0)) {
           if (use > 0) mbar_wait(FBAR(B_W_EMPTY + st), (uint32_t)((use - 1) & 1));
-          const uint32_t wb = cds[ci].w_bytes;
+          const FChunk cd = P.chunks[cb0 + ci];
+          const uint32_t wb = ((cd.meta >> 2) & 3u) * 16u * Nw * 4u;
+          if ((P.dbg_flags & 1) && use > 0) { mbar_arrive(FBAR(B_W_FULL + st)); continue; }
           mbar_expect_tx(FBAR(B_W_FULL + st), wb);
-          bulk_g2s(smem_base + P.off_ring + (uint32_t)st * F_STAGE_BYTES, op->wchunks + cds[ci].w_off, wb, FBAR(B_W_FULL + st));
+          bulk_g2s(smem_base + P.off_ring + (uint32_t)st * F_STAGE_BYTES, op->wchunks + cd.w_off, wb, FBAR(B_W_FULL + st));
         }
       }
     }
   } else if (warp == F_WARP_MMA) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      int n = 0, k = 0, nuse0 = 0, nuse1 = 0;   // items that used accumulator / in_full parity 0 / 1
+    // ================= MMA issuer: the whole warp walks the loop (uniform), one elected lane issues =================
+    // Per chunk the issuer does: one prefetched 16-byte constant load, one barrier wait, a handful of uniform adds, the
+    // MMAs and one commit -- the round-2 timeline showed the tensor pipe itself runs at its floor (bytes / 128 per MMA)
+    // and that a fat per-chunk prologue (~300 cycles of dependent uniform ALU) was what stretched the MMA phases.
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const bool dbg_on = (P.dbg != nullptr);
+      const uint32_t ring_w0 = ((smem_base + P.off_ring) >> 4) & 0x3FFFu;
+      uint32_t st = 0, ph = 0;                   // ring stage and its phase, carried across items
+      int k = 0, nuse0 = 0, nuse1 = 0;           // items that used accumulator / in_full parity 0 / 1
       F_FOR_ITEMS {
-        const FOp* op = P.ops + j;
+        const FOp* op = &P.ops[j];
         const int p = k & 1;
-        const int N = op->N, NMT = op->n_mt, big = op->big;
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t abase = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
-        const uint32_t dbase = tmem_base + (uint32_t)p * 256u;
+        const uint32_t N = (uint32_t)op->N;
+        const int NMT = op->n_mt, big = op->big;
+        const uint32_t idesc = (1u << 4) | ((N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t abase16 = (smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes)) >> 4;
+        const uint32_t dbase = tmem_u + (uint32_t)p * 256u;
+        const uint32_t b_hi = N << 16, b_kstep = 2u * N;      // LBO field of B; (2 panels * N rows * 16 B) >> 4 per K step
         const int nuse = p ? nuse1 : nuse0;
+        const int nc = op->n_chunks, cb0 = op->chunk_base;
+        FChunk cd = P.chunks[cb0];
         if (nuse > 0) mbar_wait(FBAR(B_ACC_EMPTY + p), (uint32_t)((nuse - 1) & 1));
         mbar_wait(FBAR(B_IN_FULL + p), (uint32_t)(nuse & 1));
         tc_fence_after();
-        const ChunkDesc* cds = P.chunks + op->chunk_base;
-        const int nc = op->n_chunks;
-        for (int ci = 0; ci < nc; ++ci, ++n) {
-          const ChunkDesc cd = cds[ci];
-          const int st = n % F_STAGES, use = n / F_STAGES;
-          mbar_wait(FBAR(B_W_FULL + st), (uint32_t)(use & 1));
+        if (dbg_on) FSTAMP(k, 1);
+        long long wstall = 0;
+        for (int ci = 0; ci < nc; ++ci) {
+          const FChunk nxt = P.chunks[cb0 + ci + 1];           // table is padded by one entry
+          if (dbg_on) { const long long w0 = clock64(); mbar_wait(FBAR(B_W_FULL + st), ph); wstall += clock64() - w0; }
+          else mbar_wait(FBAR(B_W_FULL + st), ph);
           tc_fence_after();
-          const uint32_t wbase = smem_base + P.off_ring + (uint32_t)st * F_STAGE_BYTES;
-          const uint32_t b_plane = (uint32_t)cd.k16 * 2u * (uint32_t)N * 16u;
-          for (int i = 0; i < NMT; ++i) {
-            const uint32_t d_tmem = dbase + (uint32_t)cd.acc * 128u + (uint32_t)(i * N);
-            const uint32_t a_row = abase + cd.a_off + (uint32_t)(2 + 128 * i + cd.d) * 16u;
-            for (int kk = 0; kk < cd.k16; ++kk) {
-              const uint32_t a_hi = a_row + (uint32_t)kk * 2u * cd.a_lbo, a_lo = a_hi + cd.a_plane;
-              const uint32_t b_hi = wbase + (uint32_t)kk * 2u * (uint32_t)N * 16u, b_lo = b_hi + b_plane;
-              const uint64_t da_hi = make_desc(a_hi, cd.a_lbo, 128), da_lo = make_desc(a_lo, cd.a_lbo, 128);
-              const uint64_t db_hi = make_desc(b_hi, (uint32_t)N * 16u, 128), db_lo = make_desc(b_lo, (uint32_t)N * 16u, 128);
-              tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (cd.first && kk == 0) ? 0u : 1u);
-              tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-              tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+          const uint32_t acc = cd.meta & 1u, first = (cd.meta >> 1) & 1u, k16 = (cd.meta >> 2) & 3u;
+          uint32_t a_w = cd.a_w + abase16;
+          uint32_t b_w = (ring_w0 + st * (F_STAGE_BYTES >> 4)) | b_hi;
+          const uint32_t a_kstep = cd.a_ks_pl & 0xFFFFu, a_pl = cd.a_ks_pl >> 16;
+          const uint32_t b_pl = k16 * b_kstep;
+          const uint32_t dt = dbase + acc * 128u;
+          for (uint32_t kk = 0; kk < k16; ++kk) {
+            const uint32_t acc0 = (first && kk == 0) ? 0u : 1u;
+            // the three terms of the hi/lo split, m-tiles innermost: consecutive MMAs write different accumulators
+            if (NMT == 1) {
+              mma_lohi(dt, a_w, b_w, idesc, acc0, leader);
+              if (!(P.dbg_flags & 2)) {
+                mma_lohi(dt, a_w + a_pl, b_w, idesc, 1u, leader);
+                mma_lohi(dt, a_w, b_w + b_pl, idesc, 1u, leader);
+              }
+            } else if (NMT == 2) {
+              mma_lohi(dt, a_w, b_w, idesc, acc0, leader);
+              mma_lohi(dt + N, a_w + 128u, b_w, idesc, acc0, leader);
+              if (!(P.dbg_flags & 2)) {
+                mma_lohi(dt, a_w + a_pl, b_w, idesc, 1u, leader);
+                mma_lohi(dt + N, a_w + 128u + a_pl, b_w, idesc, 1u, leader);
+                mma_lohi(dt, a_w, b_w + b_pl, idesc, 1u, leader);
+                mma_lohi(dt + N, a_w + 128u, b_w + b_pl, idesc, 1u, leader);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mma_lohi(dt + (uint32_t)i * N, a_w + (uint32_t)i * 128u, b_w, idesc, acc0, leader);
+              if (!(P.dbg_flags & 2)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_lohi(dt + (uint32_t)i * N, a_w + (uint32_t)i * 128u + a_pl, b_w, idesc, 1u, leader);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_lohi(dt + (uint32_t)i * N, a_w + (uint32_t)i * 128u, b_w + b_pl, idesc, 1u, leader);
+              }
             }
+            a_w += a_kstep;
+            b_w += b_kstep;
           }
-          tc_commit(FBAR(B_W_EMPTY + st));
+          if (leader) tc_commit(FBAR(B_W_EMPTY + st));
+          if (++st == F_STAGES) { st = 0; ph ^= 1u; }
+          cd = nxt;
         }
-        tc_commit(FBAR(B_ACC_FULL + p));
-        if (big) { tc_commit(FBAR(B_IN_EMPTY + 0)); tc_commit(FBAR(B_IN_EMPTY + 1)); }
-        else tc_commit(FBAR(B_IN_EMPTY + p));
+        if (leader) {
+          tc_commit(FBAR(B_ACC_FULL + p));
+          if (big) { tc_commit(FBAR(B_IN_EMPTY + 0)); tc_commit(FBAR(B_IN_EMPTY + 1)); }
+          else tc_commit(FBAR(B_IN_EMPTY + p));
+        }
+        if (dbg_on && lane == 0) {
+          FSTAMP(k, 2);
+          if (blockIdx.x == 0) P.dbg[(size_t)k * 16 + 6] = wstall;
+        }
         if (p) nuse1++; else nuse0++;
         k++;
       }
@@ -460,7 +543,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
     c.B = P.B;
     int k = 0, nuse0 = 0, nuse1 = 0;
     F_FOR_ITEMS {
-      const FOp* op = P.ops + j;
+      const FOp* op = &P.ops[j];
       const int p = k & 1;
       c.tile = (int)blockIdx.x + (2 * r_ + par) * G;
       c.img = P.by_slot ? (int)blockIdx.x * 2 + par : c.tile;
@@ -468,6 +551,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       c.prm_rb = reinterpret_cast<float*>(c.prm4 + F_MAX_N);
       c.stat = reinterpret_cast<float2*>(smem + P.off_stat + (uint32_t)p * 512);
       c.tmem = tmem_base + (uint32_t)p * 256u;
+      c.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg + (size_t)k * 16 : nullptr;
+      if (tid == 0) FSTAMP(k, 7);
       // per-channel parameters of this op while its MMAs run
       const int N = op->N;
       if (tid < N) {
@@ -479,6 +564,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       epi_bar16();
       mbar_wait(FBAR(B_ACC_FULL + p), (uint32_t)((p ? nuse1 : nuse0) & 1));
       tc_fence_after();
+      if (tid == 0) FSTAMP(k, 3);
       const uint32_t bae = FBAR(B_ACC_EMPTY + p);
       if (op->kind == TC_CONVBLOCK) {
         switch (op->variant) {
@@ -492,9 +578,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
         epi_plain(op, c, bae, P.eps);
       }
       // output image visible to the async proxy (the input producer's bulk copies) before the arrival
-      fence_proxy_async_all();
+      fence_proxy_async_global();
+      if (c.dbg) c.dbg[13] = clock64();
       __syncwarp();
       if (lane == 0) mbar_arrive(FBAR(B_OUT_DONE + par));
+      if (tid == 0) FSTAMP(k, 5);
       if (p) nuse1++; else nuse0++;
       k++;
     }
@@ -506,6 +594,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 #undef FBAR
+#undef FSTAMP
 #undef F_FOR_ITEMS
 }
 
@@ -520,8 +609,6 @@ struct FusedState {
   std::vector<TcImage> images_r;   // [j] = residual-conv image written by op j (dev == nullptr if none)
   std::vector<uint8_t*> owned;     // distinct device allocations behind the images (buffers may be shared)
   uint8_t* w_all = nullptr;
-  FOp* ops_dev = nullptr;
-  ChunkDesc* chunks_dev = nullptr;
   std::vector<FOp> ops;
   FParams prm{};
   size_t smem = 0;
@@ -532,8 +619,6 @@ static void fused_free(FusedState* s) {
   if (!s) return;
   for (auto* p : s->owned) cudaFree(p);
   cudaFree(s->w_all);
-  cudaFree(s->ops_dev);
-  cudaFree(s->chunks_dev);
   delete s;
 }
 
@@ -575,7 +660,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
   };
   if (make_image(st->images[0], 16, cfg.horizon, st->n_tiles) != MMDK_OK) return fail_free("out of memory (input image)");
 
-  std::vector<ChunkDesc> all_chunks;
+  std::vector<FChunk> all_chunks;
   struct WSrc { const float* W; int cin, ktaps, tap, ci0, CK, cout, N; uint32_t dst_off; };
   std::vector<WSrc> wsrc;
   uint32_t w_total = 0;
@@ -595,7 +680,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
     p.N = op.cout < 16 ? 16 : op.cout;
     if (p.N != 16 && p.N != 32 && p.N != 64 && p.N != 128) return fail_free("tensor-core executor: unsupported channel count");
     const int NV = p.n_mt * p.N;
-    if (NV > 128 || p.n_mt * 128 > F_PART_ROWS) return fail_free("tensor-core executor: unsupported (rows, channels) combination for this network shape");
+    if (NV > 128 || p.n_mt * 128 > F_PART_ROWS || (p.n_mt != 1 && p.n_mt != 2 && p.n_mt != 4)) return fail_free("tensor-core executor: unsupported (rows, channels) combination for this network shape");
     p.variant = FV_GENERIC;
     if (p.kind == TC_CONVBLOCK) {
       if (op.n_groups != 8) return fail_free("tensor-core executor: GroupNorm needs 8 groups");
@@ -648,10 +733,13 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
       p.src_by_tile[k] = (img == 0) ? 1 : 0;
       p.src_tile_bytes[k] = st->images[img].tile_bytes;
       p.src_smem_off[k] = off;
+      p.src_lbo[k] = (uint32_t)st->images[img].rows * 16;
+      p.src_plane[k] = (uint32_t)(st->images[img].C / 8) * st->images[img].rows * 16;
       off += (st->images[img].tile_bytes + 127) & ~127u;
       return k;
     };
-    std::vector<ChunkDesc> chunks;
+    struct HChunk { uint32_t a_off, w_off, w_bytes; int d, acc, first, k16, slot; };
+    std::vector<HChunk> chunks;
     auto add_chunks = [&](const std::vector<int>& imgs, int cin_total, int w_off_blob, int ktaps, int tap, int d, int acc,
                           bool first_in_acc) -> bool {
       int ci = 0;
@@ -663,10 +751,9 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
         const int c_here = im.C;
         for (int c0 = 0; c0 < c_here; c0 += 32) {
           const int CK = std::min(32, c_here - c0);
-          ChunkDesc cd{};
+          HChunk cd{};
           cd.a_off = p.src_smem_off[slot] + (uint32_t)(c0 / 8) * im.rows * 16;
-          cd.a_plane = (uint32_t)(im.C / 8) * im.rows * 16;
-          cd.a_lbo = (uint32_t)im.rows * 16;
+          cd.slot = slot;
           cd.w_bytes = (uint32_t)CK * p.N * 4;
           cd.w_off = w_total;
           wsrc.push_back({net->blob + w_off_blob, cin_total, ktaps, tap, ci + c0, CK, op.cout, p.N, w_total});
@@ -709,7 +796,16 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
     p.n_chunks = (int)chunks.size();
     // chunk weight offsets are relative to the op's base
     op_w_off[j] = chunks.empty() ? w_total : chunks[0].w_off;
-    for (auto& cd : chunks) { cd.w_off -= op_w_off[j]; all_chunks.push_back(cd); }
+    for (auto& cd : chunks) {
+      FChunk fc{};
+      const uint32_t lbo = p.src_lbo[cd.slot], plane = p.src_plane[cd.slot];
+      fc.a_w = (((cd.a_off + (uint32_t)((2 + cd.d) * 16)) >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+      if (((2 * lbo) >> 4) > 0xFFFFu || (plane >> 4) > 0xFFFFu) return fail_free("tensor-core executor: image too large for the packed chunk descriptor");
+      fc.a_ks_pl = ((2 * lbo) >> 4) | ((plane >> 4) << 16);
+      fc.w_off = cd.w_off - op_w_off[j];
+      fc.meta = (uint32_t)cd.acc | ((uint32_t)cd.first << 1) | ((uint32_t)cd.k16 << 2);
+      all_chunks.push_back(fc);
+    }
     p.bias = net->blob + op.b;
     p.cond_off = -1;
     if (p.kind == TC_CONVBLOCK) {
@@ -746,15 +842,10 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
     pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, w.cout, w.tap, w.ci0, w.CK, w.N,
                                               reinterpret_cast<__half*>(st->w_all + w.dst_off));
   for (int j = 0; j < n_ops; ++j) st->ops[j].wchunks = st->w_all + op_w_off[j];
-  if (cudaMalloc(&st->ops_dev, sizeof(FOp) * n_ops) != cudaSuccess ||
-      cudaMalloc(&st->chunks_dev, sizeof(ChunkDesc) * std::max<size_t>(all_chunks.size(), 1)) != cudaSuccess)
-    return fail_free("out of memory (op table)");
-  cudaMemcpyAsync(st->ops_dev, st->ops.data(), sizeof(FOp) * n_ops, cudaMemcpyHostToDevice, stream);
-  cudaMemcpyAsync(st->chunks_dev, all_chunks.data(), sizeof(ChunkDesc) * all_chunks.size(), cudaMemcpyHostToDevice, stream);
-  // the host vectors must outlive the async copies
-  if (check_cuda(cudaStreamSynchronize(stream), "tensor-core executor setup") != MMDK_OK) { fused_free(st); return MMDK_ECUDA; }
-  P.ops = st->ops_dev;
-  P.chunks = st->chunks_dev;
+  if (n_ops > F_MAX_OPS || all_chunks.size() + 1 > (size_t)F_MAX_CHUNKS) return fail_free("tensor-core executor: layer program too large for the parameter bank");
+  if (check_cuda(cudaGetLastError(), "tensor-core executor setup") != MMDK_OK) { fused_free(st); return MMDK_ECUDA; }
+  for (int j = 0; j < n_ops; ++j) P.ops[j] = st->ops[j];
+  for (size_t c = 0; c < all_chunks.size(); ++c) P.chunks[c] = all_chunks[c];
   P.n_ops = n_ops;
   P.n_tiles = st->n_tiles;
   P.B = B;
@@ -799,9 +890,11 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
     const int n = B * cfg.horizon;
     pack_input_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, B, cfg.horizon, cfg.state_dim, im.rows, im.dev, im.tile_bytes);
   }
-  FParams P = st->prm;
+  FParams& P = st->prm;   // ~16 KB: patched in place, copied once by the launch
   P.cond_row = net->cond_table + (size_t)t * net->n_cond;
   P.eps = eps;
+  P.dbg = net->fused_dbg;
+  { const char* e = getenv("MMDK_FUSED_DEBUG"); P.dbg_flags = e ? atoi(e) : 0; }
   unet_fused_kernel<<<st->grid, F_THREADS, st->smem, stream>>>(P);
   return check_cuda(cudaGetLastError(), "unet_fused_kernel launch");
 }

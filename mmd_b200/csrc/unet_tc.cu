@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 // calibrate ncu's sm__pipe_tensor_cycles_active against the issue model (N/2 cycles per instruction at M=128) and to
 // measure the real cycles per MMA for every N the UNet uses.  out[blockIdx.x] = {cycles, n_mma}.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) mma_calibrate_kernel(int N, int n_iters, int a_rows, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_calibrate_kernel(int N, int n_iters, int a_rows, int n_acc, long long* out) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_ptr;
@@ -371,23 +371,31 @@ __global__ void __launch_bounds__(128, 1) mma_calibrate_kernel(int N, int n_iter
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_ptr;
-  if (tid == 0) {
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr, 0);
+  if (warp == 0) {
+    // the whole warp walks the loop with uniform operands, the elected lane issues (same scheme as unet_fused.cu):
+    // ~2 instructions per MMA, so the measurement is the tensor pipe, not the issue loop
+    const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a0 = smem_u32(smem), b0 = a0 + (uint32_t)a_rows * 32u;
-    const uint32_t a_lbo = (uint32_t)a_rows * 16u;
+    const uint32_t a_w = ((a0 >> 4) & 0x3FFFu) | (((uint32_t)a_rows * 16u >> 4) << 16);
+    const uint32_t b_w = ((b0 >> 4) & 0x3FFFu) | ((uint32_t)N << 16);
+    const uint32_t dstep = (n_acc > 1) ? 256u / (uint32_t)(n_acc > 2 ? 2 : 1) : 0u;
     const long long t0 = clock64();
-    for (int it = 0; it < n_iters; ++it) {
-      // walk the A start address like the conv taps do (16-byte row shifts), 2 accumulators alternating
-      const uint64_t da = make_desc(a0 + (uint32_t)((it % 5) * 16), a_lbo, 128);
-      const uint64_t db = make_desc(b0, (uint32_t)N * 16u, 128);
-      tc_mma_f16(tmem_base + (uint32_t)((it & 1) * 256), da, db, idesc, it >= 2 ? 1u : 0u);
+    for (int it = 0; it < n_iters; it += 4) {
+      // walk the A start address like the conv taps do (16-byte row shifts); n_acc accumulators in rotation
+      mma_lohi(tmem_base + (n_acc > 1 ? 0u : 0u), a_w + 0, b_w, idesc, it >= 4 ? 1u : 0u, leader);
+      mma_lohi(tmem_base + (n_acc > 1 ? dstep : 0u), a_w + 1, b_w, idesc, it >= 4 ? 1u : 0u, leader);
+      mma_lohi(tmem_base + (n_acc > 2 ? 2u * dstep : 0u), a_w + 2, b_w, idesc, (it >= 4 || n_acc <= 2) ? 1u : 0u, leader);
+      mma_lohi(tmem_base + (n_acc > 2 ? 3u * dstep : (n_acc > 1 ? dstep : 0u)), a_w + 3, b_w, idesc, (it >= 4 || n_acc <= 2) ? 1u : 0u, leader);
     }
-    tc_commit(smem_u32(&bar));
+    if (leader) tc_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
     const long long t1 = clock64();
-    out[2 * blockIdx.x] = t1 - t0;
-    out[2 * blockIdx.x + 1] = n_iters;
+    if (tid == 0) {
+      out[2 * blockIdx.x] = t1 - t0;
+      out[2 * blockIdx.x + 1] = n_iters;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -664,11 +672,13 @@ int unet_tc_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_out,
   return check_cuda(cudaGetLastError(), "unpack_image_kernel");
 }
 
-int mma_calibrate(int N, int n_iters, int n_ctas, long long* out_dev, cudaStream_t stream) {
-  if (N < 16 || N > 256 || (N & 15) || n_iters < 2 || n_ctas < 1) return fail(MMDK_EINVAL, "mma_calibrate: bad arguments");
+int mma_calibrate(int N, int n_iters, int n_ctas, int n_acc, long long* out_dev, cudaStream_t stream) {
+  if (N < 16 || N > 256 || (N & 15) || n_iters < 4 || (n_iters & 3) || n_ctas < 1 || n_acc < 1 || n_acc > 4 || (n_acc > 2 && N > 128) ||
+      (n_acc > 1 && N > 256))
+    return fail(MMDK_EINVAL, "mma_calibrate: bad arguments");
   const int a_rows = 128 + 8;
   const size_t smem = (size_t)a_rows * 32 + (size_t)N * 32 + 128;
-  mma_calibrate_kernel<<<n_ctas, 128, smem, stream>>>(N, n_iters, a_rows, out_dev);
+  mma_calibrate_kernel<<<n_ctas, 128, smem, stream>>>(N, n_iters, a_rows, n_acc, out_dev);
   return check_cuda(cudaGetLastError(), "mma_calibrate_kernel");
 }
 

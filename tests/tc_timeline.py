@@ -1,36 +1,43 @@
-import sys, ctypes as C
-sys.path.insert(0, '/root/repo')
+"""Per-item timeline of CTA 0 of the persistent UNet executor (development tool; see mmdk_unet_debug_timeline)."""
+import ctypes as C
+import sys
+
 import torch
-from oracle import port
-from tests.helpers import build_product
-from mmd_b200 import _lib
-dev = torch.device('cuda:0')
-P = port.make_unet_params(seed=0)
-p = build_product(dev, "EnvEmpty2D", T=25, P=P)
-B = 4096
+
+sys.path.insert(0, ".")
+import mmd_b200 as M  # noqa: E402
+from mmd_b200 import _lib  # noqa: E402
+from oracle import port  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda:0")
+unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+unet.load_state_dict(port.make_unet_params(seed=0), strict=True)
+unet = unet.to(dev)
 x = torch.randn(B, 64, 4, device=dev)
-u = p["unet"]
-for _ in range(3): u.forward_t(x, 7, precision="f16x3")
-h = u.native(); lib = _lib.lib()
-n_tiles = (B + 6) // 7
-names = {0: 'd0.0.b0 (4->32 @64)', 3: 'd0.1.b1 (32->32 @64)', 12: 'd2.1.b0 (128->128 @16)', 15: 'mid1.b1 (128 @16, res id)', 18: 'u0.0.b0 (256->64 @16)', 25: 'u1.1.b0 (32->32 @32)', 29: 'final 1x1'}
-for op in [3, 12, 15, 18, 25, 29]:
-    dbg = torch.zeros(n_tiles, 16, dtype=torch.int64, device=dev)
-    _lib.check(lib.mmdk_unet_debug_timeline(h, op, _lib.ptr(dbg), _lib.stream_ptr()))
-    u.forward_t(x, 7, precision="f16x3"); torch.cuda.synchronize()
-    d = dbg.cpu()
-    t0 = d[:, 0]
-    rel = (d[:, 1:12] - t0[:, None]).float()
-    # choose tiles that were in the first wave on their SM: smallest t0 per smid
-    print(f"op {op} {names.get(op)}: median cycles since CTA start [prod:depwait_done, prod:done, mma:in_full, mma:last_commit, epi:before_acc_wait, epi:acc_ready, epi:pass1_done, epi:bar1, epi:stats_done, epi:end, all:after_sync]")
-    print('   ', [int(v) for v in rel.median(0).values.tolist()])
-    life = (d[:, 11] - d[:, 0]).float()
-    print('    CTA lifetime median %.0f p90 %.0f cycles' % (life.median(), life.quantile(0.9)))
-    # per-SM span: first start to last end
-    sm = d[:, 15]
-    spans = []
-    for s_ in sm.unique()[:20]:
-        m = sm == s_
-        spans.append(int(d[m, 11].max() - d[m, 0].min()))
-    print('    per-SM span (first 20 SMs) median', sorted(spans)[len(spans)//2], 'tiles/SM', float(m.sum()))
-_lib.check(lib.mmdk_unet_debug_timeline(h, -1, None, _lib.stream_ptr()))
+for _ in range(3):
+    unet.forward_t(x, 5, precision="f16x3")
+n_items = 33 * 4
+dbg = torch.zeros(n_items, 16, dtype=torch.int64, device=dev)
+lib = _lib.lib()
+_lib.check(lib.mmdk_unet_debug_timeline(unet.native(), -2, _lib.ptr(dbg), _lib.stream_ptr()))
+unet.forward_t(x, 5, precision="f16x3")
+torch.cuda.synchronize()
+_lib.check(lib.mmdk_unet_debug_timeline(unet.native(), -2, None, _lib.stream_ptr()))
+d = dbg.cpu()
+t0 = int(d[0, 0])
+print("item op par | load_issue  in_ready(+load)  mma_issued(+mma)  [w_stall]  acc_ready  epi_start..epi_done(+epi) | period")
+prev_done = None
+for k in range(n_items):
+    if int(d[k, 0]) == 0:
+        break
+    j, par = (k // 2) % 33, k % 2
+    li, ir, mi, ar, ed, ws, es = [int(d[k, i]) for i in (0, 1, 2, 3, 5, 6, 7)]
+    e = [int(d[k, i]) for i in (8, 9, 10, 11, 12, 13)]
+    st = max(es, ar)
+    phases = (f" epi: tmem {e[0] - st:5d} stats {e[1] - e[0]:5d} bar {e[2] - e[1]:5d} reduce+bar {e[3] - e[2]:5d} norm {e[4] - e[3]:5d} "
+              f"fence {e[5] - e[4]:5d}") if e[0] else ""
+    print(f"{k:4d} {j:2d} {par} | {li - t0:8d} {ir - t0:8d} (+{ir - li:5d}) {mi - t0:8d} (+{mi - ir:5d}) [{ws:5d}] {ar - t0:8d} "
+          f"{st - t0:8d}..{ed - t0:8d} (+{ed - st:5d}) | {'' if prev_done is None else ed - prev_done}{phases}")
+    prev_done = ed
+print("total cycles CTA 0:", int(d[:k, 5].max()) - t0)
