@@ -217,6 +217,22 @@ int mmdk_cell_index(const mmdk_guide_env* env, const float* points_dev, int64_t 
 int mmdk_check_rr_collisions(const float* pos_dev, int64_t n_batch, int R, float margin, uint8_t* coll_dev,
                              float* mid_dev, void* stream);
 
+/* CBS.get_conflicts (mmd/planners/multi_agent/cbs.py:166-246) for n_cand candidate joint states at once -- the
+ * 'least_collisions' strategy re-runs it once per free sample (cbs.py:446-458).  base_paths_dev [R, T, 2]: the (globally
+ * padded, multi_agent_utils.py:120-143) best path positions of every robot; cand_paths_dev [n_cand, T, 2]: candidate paths
+ * of robot `agent_id` (NULL with n_cand = 1: the base state itself).  Paths are densified on the fly exactly like
+ * densify_trajs (trajectory_utils.py:54-69; densify = 1: identity, 2 when edge conflicts are requested), T_dense =
+ * (T - 1) * densify + 1.  Outputs: coll_dev [n_cand, T_dense, R, R] uint8 as check_rr_collisions returns it (margin =
+ * 2.1 r), count_dev [n_cand] int32 = number of (t, a, b) rows torch.nonzero would list (NULL to skip), dense_dev
+ * [n_cand, R, T_dense, 2] the densified positions (NULL to skip).  Bit-exact with the reference. */
+int mmdk_get_conflicts(const float* base_paths_dev, const float* cand_paths_dev, int n_cand, int agent_id, int R, int T,
+                       int densify, float margin, uint8_t* coll_dev, int32_t* count_dev, float* dense_dev, void* stream);
+
+/* smooth_trajs (mmd/common/trajectory_utils.py:31-38: scipy.signal.savgol_filter(window 10, polyorder 2, mode 'interp')
+ * along the horizon of trajs_dev [B, H, D]) as one linear operator filter_dev [H, H] float64 built by the host
+ * (mmd_b200/smoothing.py restates scipy's coefficients and its polynomial edge fit); double accumulation, fp32 out. */
+int mmdk_smooth_trajs(const double* filter_dev, const float* trajs_dev, int B, int H, int D, float* out_dev, void* stream);
+
 /* PlanningTask.get_trajs_collision_and_free + cost_smoothness/path_length (TR/tasks/tasks.py:236-311,
  * TR/trajectory/metrics.py:7-39, mpd.py:356-382) on UNNORMALISED trajectories trajs_dev [B, H, D]:
  * free_dev [B] uint8 (no interpolated waypoint in collision AND inside joint limits), cost_dev [B] =

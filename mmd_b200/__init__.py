@@ -14,3 +14,6 @@ from .datasets import LimitsNormalizer, TrajectoryDataset  # noqa: F401
 from .sampler import MultiRobotSampler  # noqa: F401
 from .planners import MPD, DiffusionsEnsemble, MultiPointConstraint, PlannerOutput  # noqa: F401
 from . import envs  # noqa: F401
+from . import conflicts, smoothing  # noqa: F401
+from .conflicts import get_conflicts, count_conflicts_batched, global_pad_paths  # noqa: F401
+from .smoothing import smooth_trajs  # noqa: F401

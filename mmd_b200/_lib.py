@@ -53,7 +53,7 @@ class StepScalars(C.Structure):
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
     "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
-    "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize",
+    "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize", "mmdk_get_conflicts", "mmdk_smooth_trajs",
 ]
 
 _lib = None
@@ -93,6 +93,8 @@ def load():
     lib.mmdk_cell_index.argtypes = [C.POINTER(GuideEnv), vp, i64, vp, vp]
     lib.mmdk_check_rr_collisions.argtypes = [vp, i64, i, f, vp, vp, vp]
     lib.mmdk_classify_trajs.argtypes = [C.POINTER(GuideEnv), vp, i, i, i, f, C.c_float * 2, C.c_float * 2, vp, vp, vp, vp]
+    lib.mmdk_get_conflicts.argtypes = [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp]
+    lib.mmdk_smooth_trajs.argtypes = [vp, vp, i, i, i, vp, vp]
     lib.mmdk_unnormalize.argtypes = [C.POINTER(GuideEnv), vp, i64, i, vp, vp]
     _lib = lib
     return lib

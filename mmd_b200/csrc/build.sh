@@ -6,13 +6,13 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH --expt-relaxed-constexpr"
 mkdir -p ../_build
-SRCS="api unet unet_tc unet_fused guide"
+SRCS="api unet unet_tc unet_fused guide post"
 pids=()
 for f in $SRCS; do
   rm -f ../_build/$f.o            # a failed compile must never leave a stale object for the link step
   extra=""
-  # guide.cu reproduces the reference's op-by-op fp32 arithmetic: no FMA contraction
-  if [ "$f" = guide ]; then extra="-fmad=false"; fi
+  # guide.cu / post.cu reproduce the reference's op-by-op fp32 arithmetic: no FMA contraction
+  if [ "$f" = guide ] || [ "$f" = post ]; then extra="-fmad=false"; fi
   $NVCC $COMMON $extra -c $f.cu -o ../_build/$f.o "$@" &
   pids+=($!)
 done

@@ -2,8 +2,8 @@
 
 Reference: mmd/planners/single_agent/mpd.py:58-520, mmd/planners/single_agent/common.py:26-46,
 mmd/models/diffusion_models/diffusion_ensemble.py:25-312.  Host logic only; every tensor op is a libmmdk kernel
-(UNet, fused DDPM/guide step, classification, unnormalise) except the final argmin over K costs and the optional
-Savitzky-Golay smoothing, which the reference also runs on the host through scipy (trajectory_utils.py:31-38).
+(UNet, fused DDPM/guide step, classification, unnormalise) except the final argmin over K costs and the Savitzky-Golay
+smoothing now runs on the device too (smoothing.py).
 """
 import math
 import time
@@ -46,19 +46,7 @@ class PlannerOutput:  # common.py:26-46
         self.constraints_l = None
 
 
-def smooth_trajs(trajs, window_size=10, poly_order=2):
-    """mmd/common/trajectory_utils.py:31-38: scipy savgol on the host, exactly as the reference (next row 8f-3)."""
-    try:
-        from scipy.signal import savgol_filter
-    except Exception:  # scipy missing: leave unsmoothed rather than guess
-        return trajs
-    out = trajs.clone()
-    t = trajs.detach().cpu().numpy()
-    for i in range(t.shape[0]):
-        for d in range(t.shape[-1]):
-            t[i, :, d] = savgol_filter(t[i, :, d], window_size, poly_order)
-    out.copy_(torch.from_numpy(t).to(trajs.device))
-    return out
+from .smoothing import smooth_trajs  # noqa: E402  (trajectory_utils.py:31-38 on the device: mmdk_smooth_trajs)
 
 
 class MPD:

@@ -776,3 +776,62 @@ def hard_conds_from_start_goal(start_pos, goal_pos, normalizer: LimitsNormalizer
     s = normalizer.normalize(torch.cat((start_pos, torch.zeros_like(start_pos))))
     g = normalizer.normalize(torch.cat((goal_pos, torch.zeros_like(goal_pos))))
     return {0: s, horizon - 1: g}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conflict detection (mmd/planners/multi_agent/cbs.py:166-246) and post-smoothing (mmd/common/trajectory_utils.py:31-69)
+# ---------------------------------------------------------------------------------------------------------------------
+def global_pad_paths(path_l, start_time_l):  # mmd/common/multi_agent_utils.py:120-143
+    if len(path_l) == 0:
+        return []
+    max_t = max(len(p) + start_time_l[i] for i, p in enumerate(path_l))
+    out = []
+    for i, p in enumerate(path_l):
+        if len(p) + start_time_l[i] < max_t:
+            p = torch.cat([p, p[-1].repeat(max_t - len(p) - start_time_l[i], 1)])
+        if start_time_l[i] > 0:
+            p = torch.cat([p[0].repeat(start_time_l[i], 1), p])
+        out.append(p)
+    return out
+
+
+def densify_trajs(trajs, n_points_interp=10):  # trajectory_utils.py:54-69 (Python loops, kept verbatim in structure)
+    out = []
+    for traj in trajs:
+        d = []
+        for i in range(traj.shape[0] - 1):
+            d.append(traj[i])
+            for j in range(1, n_points_interp):
+                d.append(traj[i] + j * (traj[i + 1] - traj[i]) / n_points_interp)
+        d.append(traj[-1])
+        out.append(torch.stack(d))
+    return out
+
+
+def get_conflicts(best_path_l, start_time_l, want_vertex=False, want_edge=False, want_point=True, radius=ROBOT_RADIUS):
+    """cbs.py:166-246 -> list of tuples in the reference's order:
+    ("vertex", a, b, t) / ("edge", a, b, t_from, t_to) / ("point", a, b, t_from, t_to, p_a, p_b, midpoint)."""
+    import math
+    best_path_l = global_pad_paths(list(best_path_l), start_time_l)
+    paths_pos_l = [p[..., :2] for p in best_path_l]
+    if len(paths_pos_l) == 0:
+        return []
+    factor = 2 if want_edge else 1
+    dense_l = densify_trajs(paths_pos_l, factor)
+    b = torch.stack(dense_l).permute(1, 0, 2)
+    coll, pts = check_rr_collisions(b, radius)
+    out = []
+    for t_dense, a, bb in torch.nonzero(coll.int()).tolist():
+        t_from, t_to = math.floor(t_dense / factor), math.ceil(t_dense / factor)
+        if want_vertex and t_from == t_to:
+            out.append(("vertex", a, bb, t_from))
+        if want_edge and t_from != t_to:
+            out.append(("edge", a, bb, t_from, t_to))
+        if want_point:
+            out.append(("point", a, bb, t_from, t_to, dense_l[a][t_dense], dense_l[bb][t_dense], pts[t_dense, a, bb]))
+    return out
+
+
+def smooth_trajs(trajs, window_size=10, poly_order=2):  # trajectory_utils.py:31-38 (scipy on the host, as the reference)
+    from scipy.signal import savgol_filter
+    return torch.tensor(savgol_filter(trajs.cpu().numpy(), window_size, poly_order, axis=1))

@@ -504,3 +504,55 @@ def test_peer_table_sizes_cross_smem_boundary(pair, dev, n_peers):
         ref = o["guide"](x[sl])
         o["guide"].extra = []
         assert max_err(out["hash"][sl], ref) < 1e-6, (n_peers, r)
+
+
+@pytest.mark.parametrize("kinds", [("point",), ("vertex", "edge", "point")])
+def test_get_conflicts_bit_exact(dev, kinds):
+    """CBS.get_conflicts on the device (densification + pairwise test in one kernel): same conflicts, same order, same
+    positions as the oracle (cbs.py:166-246), ragged start times included."""
+    import mmd_b200 as M
+    from mmd_b200.conflicts import EdgeConflict, PointConflict, VertexConflict
+    from tests.test_oracle_vs_reference import _crossing_paths
+    paths = _crossing_paths(R=7, seed=3)
+    starts = [0, 2, 0, 1, 0, 3, 0]
+    paths = [p[: 64 - s] for p, s in zip(paths, starts)]
+    types = tuple({"point": PointConflict, "vertex": VertexConflict, "edge": EdgeConflict}[k] for k in kinds)
+    ref = port.get_conflicts(paths, starts, want_vertex="vertex" in kinds, want_edge="edge" in kinds, want_point="point" in kinds)
+    out = M.get_conflicts([p.to(dev) for p in paths], starts, conflict_types=types)
+    assert len(ref) == len(out) and len(ref) > 0
+    for r, o in zip(ref, out):
+        assert o.agent_ids == [r[1], r[2]]
+        if r[0] == "vertex":
+            assert isinstance(o, VertexConflict) and o.t == r[3]
+        elif r[0] == "edge":
+            assert isinstance(o, EdgeConflict) and (o.t_from, o.t_to) == (r[3], r[4])
+        else:
+            assert isinstance(o, PointConflict) and (o.t_from, o.t_to) == (r[3], r[4])
+            assert torch.equal(o.agent_id_to_p[r[1]].cpu(), r[5]) and torch.equal(o.agent_id_to_p[r[2]].cpu(), r[6])
+            assert torch.equal(o.agent_id_to_q[r[1]].cpu(), r[7])
+
+
+def test_count_conflicts_batched_equals_per_sample_calls(dev):
+    """cbs.py:446-458: one get_conflicts call per candidate sample of one agent == one batched kernel call."""
+    import mmd_b200 as M
+    from tests.test_oracle_vs_reference import _crossing_paths
+    R, K = 6, 40
+    paths = _crossing_paths(R=R, seed=5)
+    starts = [0] * R
+    g = torch.Generator().manual_seed(9)
+    cands = paths[2][None] + torch.cat((0.05 * torch.randn(K, 64, 2, generator=g), torch.zeros(K, 64, 2)), -1)
+    counts, _ = M.count_conflicts_batched([p.to(dev) for p in paths], starts, 2, cands.to(dev))
+    ref = []
+    for k in range(K):
+        pl = list(paths)
+        pl[2] = cands[k]
+        ref.append(len(port.get_conflicts(pl, starts)))
+    assert counts.cpu().tolist() == ref and max(ref) > min(ref)
+
+
+def test_smooth_trajs_matches_scipy(dev):
+    import mmd_b200 as M
+    x = torch.randn(33, 64, 4, generator=torch.Generator().manual_seed(2))
+    ref = port.smooth_trajs(x)          # scipy savgol_filter in fp32, exactly the reference's call
+    out = M.smooth_trajs(x.to(dev))
+    assert max_err(out, ref) < 5e-6     # scipy's own fp32 rounding is ~1.5e-6 against the exact operator

@@ -95,3 +95,20 @@ def test_executor_selection():
                           self_attention=True).resolve_precision() == "fp32"
     u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4), unet_precision="fp32")
     assert u.resolve_precision() == "fp32" and u.resolve_precision("f16x3") == "f16x3"
+
+
+def test_savgol_matrix_equals_scipy():
+    """mmd_b200.smoothing restates scipy's savgol_filter(mode='interp') as one matrix (no scipy at run time)."""
+    import numpy as np
+    from scipy.signal import savgol_filter
+    from mmd_b200.smoothing import savgol_matrix
+    for n, w, p in [(64, 10, 2), (64, 11, 2), (20, 10, 2), (64, 9, 3), (10, 10, 2)]:
+        assert np.abs(savgol_matrix(n, w, p) - savgol_filter(np.eye(n), w, p, axis=0)).max() < 1e-12, (n, w, p)
+
+
+def test_global_pad_paths_equals_oracle():
+    import mmd_b200 as M
+    paths = [torch.randn(60, 4), torch.randn(64, 4), torch.randn(61, 4)]
+    starts = [4, 0, 1]
+    for a, b in zip(M.global_pad_paths(paths, starts), port.global_pad_paths(paths, starts)):
+        assert torch.equal(a, b)

@@ -88,3 +88,52 @@ def test_lockstep_oracle_is_a_composition_of_reference_calls(ref):
         xs = new
         k += 1
     assert torch.equal(torch.stack(xs), out)
+
+
+def _crossing_paths(R=5, H=64, seed=0, spread=0.5):
+    """Straight lines through the origin region + noise: several robots meet near the centre (conflicts exist)."""
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.arange(R, dtype=torch.float32) * (2 * 3.14159265 / R)
+    start = torch.stack((torch.cos(ang), torch.sin(ang)), -1) * spread
+    t = torch.linspace(0, 1, H)[None, :, None]
+    pos = start[:, None, :] * (1 - 2 * t) + 0.004 * torch.randn(R, H, 2, generator=g)
+    return [torch.cat((p, torch.zeros(H, 2)), -1) for p in pos]
+
+
+@pytest.mark.parametrize("kinds", [("point",), ("vertex", "edge"), ("vertex", "edge", "point")])
+def test_get_conflicts_matches_reference(kinds):
+    """oracle.port.get_conflicts against the reference's own CBS.get_conflicts (cbs.py:166-246) called unbound on a stub
+    `self` (the method reads only reference_robot, start_time_l and conflict_type_to_constraint_types)."""
+    import types
+    from mmd.common.conflicts import EdgeConflict, PointConflict, VertexConflict
+    from mmd.planners.multi_agent.cbs import CBS
+    from torch_robotics.robots import RobotPlanarDisk
+    paths = _crossing_paths()
+    start_times = [0, 2, 0, 1, 0]
+    paths = [p[: 64 - s] for p, s in zip(paths, start_times)]   # ragged: different start times, same end time
+    robot = RobotPlanarDisk(tensor_args={"device": torch.device("cpu"), "dtype": torch.float32})
+    cmap = {}
+    if "point" in kinds: cmap[PointConflict] = []
+    if "vertex" in kinds: cmap[VertexConflict] = []
+    if "edge" in kinds: cmap[EdgeConflict] = []
+    stub = types.SimpleNamespace(reference_robot=robot, start_time_l=start_times, conflict_type_to_constraint_types=cmap)
+    state = types.SimpleNamespace(path_bl=[p[None] for p in paths], ix_best_path_in_batch_l=[0] * len(paths))
+    ref = CBS.get_conflicts(stub, state)
+    out = port.get_conflicts(paths, start_times, want_vertex="vertex" in kinds, want_edge="edge" in kinds,
+                             want_point="point" in kinds)
+    assert len(ref) == len(out) and len(ref) > 0
+    for r, o in zip(ref, out):
+        assert r.agent_ids == [o[1], o[2]]
+        if isinstance(r, VertexConflict):
+            assert o[0] == "vertex" and r.t == o[3]
+        elif isinstance(r, EdgeConflict):
+            assert o[0] == "edge" and (r.t_from, r.t_to) == (o[3], o[4])
+        else:
+            assert o[0] == "point" and (r.t_from, r.t_to) == (o[3], o[4])
+            assert torch.equal(r.agent_id_to_p[o[1]], o[5]) and torch.equal(r.agent_id_to_q[o[1]], o[7])
+
+
+def test_smooth_trajs_matches_reference():
+    from mmd.common.trajectory_utils import smooth_trajs
+    x = torch.randn(6, 64, 4, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(smooth_trajs(x), port.smooth_trajs(x))
