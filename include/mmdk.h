@@ -185,6 +185,27 @@ typedef struct {
 int mmdk_ddpm_step(const mmdk_guide_env* env, const mmdk_groups* groups, const mmdk_step_scalars* sc, int H,
                    float* x_dev, const float* eps_dev, const float* noise_dev, float* chain_dev, void* stream);
 
+/* The whole reverse loop of p_sample_loop (diffusion_model_base.py:163-211) in ONE call: for every step i
+ *   [lockstep, guided steps only: mmdk_publish_peers -> mmdk_build_peer_hash]  ->  mmdk_unet_forward(t_index[i])  ->
+ *   mmdk_ddpm_step(scalars[i], noise frame i, chain frame i)
+ * issued natively on `stream`; with use_graph != 0 the sequence is captured once into a CUDA graph (keyed on every pointer
+ * and scalar it bakes in) and replayed, so a chain costs one graph launch.  noise_dev [n_steps, B, H, D] step-major (NULL:
+ * no noise added), chain_out_dev [n_steps, B, H, D] (NULL: keep only x_dev), eps_dev [B, H, D] scratch.  Lock-step with
+ * the fleet sharded over several processes needs an exchange between publication and hash build: that path stays in the
+ * host loop (mmd_b200/sampler.py); peers_local_dev = the rows of groups->peers_dev that belong to this call's groups. */
+typedef struct {
+  int n_steps;
+  const int* t_index;                 /* [n_steps] timestep fed to the UNet (max(i, 0), sample_functions.py:51-54) */
+  const mmdk_step_scalars* scalars;   /* [n_steps] */
+  int lockstep;
+  int rep_index;
+  float* peers_local_dev;
+} mmdk_chain_desc;
+
+int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* env, const mmdk_groups* groups,
+                   const mmdk_chain_desc* chain, int H, float* x_dev, float* eps_dev, const float* noise_dev,
+                   float* chain_out_dev, int use_graph, void* stream);
+
 /* Publishes the representative sample of every group for the lock-step exchange: peers_out_dev[g] [H,2] =
  * unnormalise(x[g*K + rep_index])[:, :2] with the normaliser's clip rule applied to that group. */
 int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, int rep_index, const float* x_dev,

@@ -49,10 +49,15 @@ class StepScalars(C.Structure):
                 ("final_hard_conds", C.c_int)]
 
 
+class ChainDesc(C.Structure):
+    _fields_ = [("n_steps", C.c_int), ("t_index", C.POINTER(C.c_int)), ("scalars", C.POINTER(StepScalars)),
+                ("lockstep", C.c_int), ("rep_index", C.c_int), ("peers_local_dev", C.c_void_p)]
+
+
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
-    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
+    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize", "mmdk_get_conflicts", "mmdk_smooth_trajs",
 ]
 
@@ -86,6 +91,7 @@ def load():
     lib.mmdk_debug_mma_calibrate.argtypes = [i, i, i, i, vp, vp]
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
+    lib.mmdk_run_chain.argtypes = [vp, i, C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(ChainDesc), i, vp, vp, vp, vp, i, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]
     lib.mmdk_build_peer_hash.argtypes = [vp, i, i, i, f, f, vp, vp, vp]
     lib.mmdk_cross_condition.argtypes = [vp, vp, i, i, i, i, C.c_float * 4, C.c_float * 4, vp]

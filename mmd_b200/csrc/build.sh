@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH --expt-relaxed-constexpr"
 mkdir -p ../_build
-SRCS="api unet unet_tc unet_fused guide post"
+SRCS="api unet unet_tc unet_fused guide post chain"
 pids=()
 for f in $SRCS; do
   rm -f ../_build/$f.o            # a failed compile must never leave a stale object for the link step

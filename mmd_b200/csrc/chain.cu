@@ -1,0 +1,157 @@
+// Whole reverse chain behind ONE C call: the per-timestep loop of p_sample_loop (diffusion_model_base.py:163-211 ->
+// sample_functions.py:41-86) with every step's launches (lock-step peer publication + hash, TemporalUnet forward, fused
+// posterior/guide/noise step) issued natively, optionally captured once into a CUDA graph and replayed.
+//
+// Why: at B = R*K = 4096 a reverse step is ~1.4 ms of GPU work and the Python loop's ~6 ctypes launches per step are hidden;
+// at the planner's B = K = 64..128 (one MPD.__call__) or with the fleet sharded 8 ways (512 trajectories per GPU) a step
+// is ~0.2 ms and the host loop is the bottleneck.  One graph launch per chain removes it.
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mmdk {
+
+namespace {
+
+struct GraphKey {
+  std::vector<uint64_t> words;
+  bool operator<(const GraphKey& o) const { return words < o.words; }
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t last_use = 0;
+};
+
+struct ChainCache {
+  std::map<GraphKey, GraphEntry> graphs;
+  cudaStream_t side = nullptr;       // capture / replay stream (the caller's stream may be the legacy default stream,
+  cudaEvent_t ev_in = nullptr;       // which cannot be captured); ordered with the caller's stream through events
+  cudaEvent_t ev_out = nullptr;
+  uint64_t tick = 0;
+};
+
+ChainCache& cache_for_device(int dev) {
+  static std::map<int, ChainCache> caches;
+  return caches[dev];
+}
+
+void push_bytes(GraphKey& k, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; i += 8) {
+    uint64_t w = 0;
+    for (size_t j = 0; j < 8 && i + j < n; ++j) w |= (uint64_t)b[i + j] << (8 * j);
+    k.words.push_back(w);
+  }
+}
+
+}  // namespace
+
+static int issue_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* env, const mmdk_groups* groups,
+                       const mmdk_chain_desc* ch, int H, float* x, float* eps, const float* noise, float* chain_out,
+                       cudaStream_t s) {
+  const size_t B = (size_t)groups->n_groups * groups->K;
+  const size_t frame = B * H * MMDK_STATE_DIM;
+  for (int i = 0; i < ch->n_steps; ++i) {
+    const mmdk_step_scalars& sc = ch->scalars[i];
+    if (ch->lockstep && sc.n_guide_steps > 0 && groups->n_peers > 1 && groups->peers_dev) {
+      // every group publishes its representative sample into its row of the peer table (single rank: the table IS local)
+      int rc = mmdk_publish_peers(env, groups->n_groups, groups->K, H, ch->rep_index, x, ch->peers_local_dev, s);
+      if (rc != MMDK_OK) return rc;
+      if (groups->peer_cell_start_dev) {
+        rc = mmdk_build_peer_hash(groups->peers_dev, groups->n_peers, H, groups->peer_grid, groups->peer_grid_lo,
+                                  groups->peer_grid_inv_cell, const_cast<uint16_t*>(groups->peer_cell_start_dev),
+                                  const_cast<float*>(groups->peer_sorted_dev), s);
+        if (rc != MMDK_OK) return rc;
+      }
+    }
+    int rc = mmdk_unet_forward(net, unet_mode, x, (int)B, ch->t_index[i], eps, s);
+    if (rc != MMDK_OK) return rc;
+    rc = mmdk_ddpm_step(env, groups, &sc, H, x, eps, noise ? noise + (size_t)i * frame : nullptr,
+                        chain_out ? chain_out + (size_t)i * frame : nullptr, s);
+    if (rc != MMDK_OK) return rc;
+  }
+  return MMDK_OK;
+}
+
+}  // namespace mmdk
+
+using namespace mmdk;
+
+extern "C" {
+
+int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* env, const mmdk_groups* groups,
+                   const mmdk_chain_desc* chain, int H, float* x_dev, float* eps_dev, const float* noise_dev,
+                   float* chain_out_dev, int use_graph, void* stream) {
+  if (!net || !env || !groups || !chain || !x_dev || !eps_dev) return fail(MMDK_EINVAL, "null argument");
+  if (chain->n_steps < 1 || !chain->scalars || !chain->t_index) return fail(MMDK_EINVAL, "empty chain description");
+  if (chain->lockstep && groups->peers_dev && !chain->peers_local_dev) return fail(MMDK_EINVAL, "lockstep needs peers_local_dev");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!use_graph) return issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, s);
+
+  int dev = 0;
+  MMDK_CUDA(cudaGetDevice(&dev));
+  ChainCache& cc = cache_for_device(dev);
+  if (!cc.side) {
+    MMDK_CUDA(cudaStreamCreateWithFlags(&cc.side, cudaStreamNonBlocking));
+    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_in, cudaEventDisableTiming));
+    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_out, cudaEventDisableTiming));
+  }
+  // the graph bakes in every pointer and scalar: key on all of them
+  GraphKey key;
+  key.words.push_back((uint64_t)(uintptr_t)net);
+  key.words.push_back((uint64_t)unet_mode | ((uint64_t)H << 8) | ((uint64_t)chain->n_steps << 24) | ((uint64_t)chain->lockstep << 48) |
+                      ((uint64_t)chain->rep_index << 49));
+  key.words.push_back((uint64_t)(uintptr_t)x_dev);
+  key.words.push_back((uint64_t)(uintptr_t)eps_dev);
+  key.words.push_back((uint64_t)(uintptr_t)noise_dev);
+  key.words.push_back((uint64_t)(uintptr_t)chain_out_dev);
+  key.words.push_back((uint64_t)(uintptr_t)chain->peers_local_dev);
+  push_bytes(key, env, sizeof(*env));
+  push_bytes(key, groups, sizeof(*groups));
+  push_bytes(key, chain->scalars, sizeof(mmdk_step_scalars) * chain->n_steps);
+  push_bytes(key, chain->t_index, sizeof(int) * chain->n_steps);
+
+  // everything below runs on the side stream, ordered after the caller's pending work on `s`
+  MMDK_CUDA(cudaEventRecord(cc.ev_in, s));
+  MMDK_CUDA(cudaStreamWaitEvent(cc.side, cc.ev_in, 0));
+  auto it = cc.graphs.find(key);
+  if (it == cc.graphs.end()) {
+    // warm everything that allocates or configures (executor state per batch size, function attributes) OUTSIDE the capture
+    const int B = groups->n_groups * groups->K;
+    int rc = mmdk_unet_forward(net, unet_mode, x_dev, B, chain->t_index[0], eps_dev, cc.side);
+    if (rc != MMDK_OK) return rc;
+    {
+      mmdk_step_scalars dry = chain->scalars[0];
+      dry.n_guide_steps = 0; dry.do_posterior = 0; dry.add_noise = 0; dry.final_hard_conds = 0;   // x <- x: configures the launch only
+      rc = mmdk_ddpm_step(env, groups, &dry, H, x_dev, nullptr, nullptr, nullptr, cc.side);
+      if (rc != MMDK_OK) return rc;
+    }
+    MMDK_CUDA(cudaStreamSynchronize(cc.side));
+    MMDK_CUDA(cudaStreamBeginCapture(cc.side, cudaStreamCaptureModeThreadLocal));
+    rc = issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, cc.side);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cc.side, &graph);
+    if (rc != MMDK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    MMDK_CUDA(ce);
+    GraphEntry ge;
+    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    MMDK_CUDA(ce);
+    if (cc.graphs.size() >= 8) {   // bounded: evict the least recently used graph
+      auto victim = cc.graphs.begin();
+      for (auto j = cc.graphs.begin(); j != cc.graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+      cudaGraphExecDestroy(victim->second.exec);
+      cc.graphs.erase(victim);
+    }
+    it = cc.graphs.emplace(key, ge).first;
+  }
+  it->second.last_use = ++cc.tick;
+  MMDK_CUDA(cudaGraphLaunch(it->second.exec, cc.side));
+  MMDK_CUDA(cudaEventRecord(cc.ev_out, cc.side));
+  MMDK_CUDA(cudaStreamWaitEvent(s, cc.ev_out, 0));
+  return MMDK_OK;
+}
+
+}  // extern "C"

@@ -36,6 +36,7 @@ struct StepArgs {
   float* raw_out;
   int n_costs_max;
   int peers_in_smem;  // the [n_peers, H, 2] table is staged in shared memory once per launch (it is constant during it)
+  int hash_in_smem;   // the peer hash (cell_start + sorted) is staged in shared memory once per launch
 };
 
 __device__ __forceinline__ void clip_by_norm(float g[4], float max_norm) {
@@ -68,8 +69,11 @@ __device__ __forceinline__ void peer_cell(float lo, float inv_cell, int G, float
 }
 
 template <bool TAPS>
-__global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
-  extern __shared__ float4 s_xu[];   // [spc][H] unnormalised states of this CTA's samples
+__global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
+  // 512 threads (8 samples at H = 64), two CTAs per SM, clusters of up to 16: 512 CTAs of the 32 x 128 bench batch are
+  // exactly two waves of 16 clusters x 16 CTAs (round 2: 1024-thread CTAs in clusters of 8 kept only 15 clusters = 120 SMs
+  // resident and needed three waves for 2.13 waves of work)
+  extern __shared__ float4 s_xu_all[];   // [2][spc][H] unnormalised states of this CTA's samples, double buffered
   __shared__ int s_flags[2][16];     // per-iteration clip flags of the cluster's CTAs (double buffered)
 
   const int H = a.H;
@@ -122,10 +126,19 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
   else __syncthreads();
 
   // lock-step peers: constant for the whole launch -> one coalesced copy into shared memory, 20 x reuse
-  float2* s_peers = reinterpret_cast<float2*>(s_xu + (size_t)a.spc * H);
+  float2* s_peers = reinterpret_cast<float2*>(s_xu_all + 2 * (size_t)a.spc * H);
+  float4* s_sorted = reinterpret_cast<float4*>(s_peers);                                  // hash staging aliases the
+  unsigned short* s_cs = reinterpret_cast<unsigned short*>(s_sorted + (size_t)H * a.grp.n_peers);   // brute-force staging
   if (a.grp.peers_dev && a.peers_in_smem && !a.grp.peer_cell_start_dev) {
     const float2* gp = reinterpret_cast<const float2*>(a.grp.peers_dev);
     for (int i = tid; i < a.grp.n_peers * H; i += blockDim.x) s_peers[i] = __ldg(gp + i);
+    __syncthreads();
+  }
+  if (a.hash_in_smem) {
+    const int G2 = a.grp.peer_grid * a.grp.peer_grid + 1;
+    const float4* gs = reinterpret_cast<const float4*>(a.grp.peer_sorted_dev);
+    for (int i = tid; i < H * a.grp.n_peers; i += blockDim.x) s_sorted[i] = __ldg(gs + i);
+    for (int i = tid; i < H * G2; i += blockDim.x) s_cs[i] = a.grp.peer_cell_start_dev[i];
     __syncthreads();
   }
   const int n_iter = TAPS ? 1 : a.sc.n_guide_steps;
@@ -158,6 +171,9 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
       v = (v + 1.f) / 2.f;
       xu[d] = v * E.norm_range[d] + E.norm_min[d];
     }
+    // double buffered: the barrier at the top of the NEXT iteration (clip flag) separates this iteration's neighbour
+    // reads from the writes two iterations later, so no barrier is needed at the end of an iteration
+    float4* s_xu = s_xu_all + (size_t)(it & 1) * a.spc * H;
     s_xu[sl * H + h] = make_float4(xu[0], xu[1], xu[2], xu[3]);
     __syncthreads();
 
@@ -259,8 +275,8 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
       const float r2_far = r * r * 1.0001f;
       if (a.grp.peer_cell_start_dev) {
         const int G = a.grp.peer_grid;
-        const unsigned short* cs = a.grp.peer_cell_start_dev + (size_t)h * (G * G + 1);
-        const float4* sp = reinterpret_cast<const float4*>(a.grp.peer_sorted_dev) + (size_t)h * a.grp.n_peers;
+        const unsigned short* cs = (a.hash_in_smem ? s_cs : a.grp.peer_cell_start_dev) + (size_t)h * (G * G + 1);
+        const float4* sp = (a.hash_in_smem ? s_sorted : reinterpret_cast<const float4*>(a.grp.peer_sorted_dev)) + (size_t)h * a.grp.n_peers;
         int cx, cy;
         peer_cell(a.grp.peer_grid_lo, a.grp.peer_grid_inv_cell, G, xu[0], xu[1], cx, cy);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G - 1);
@@ -268,13 +284,13 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
         for (int yy = y0; yy <= y1; ++yy) {
           const int e0 = cs[yy * G + x0], e1 = cs[yy * G + x1 + 1];
           for (int e = e0; e < e1; ++e) {
-            const float4 q = __ldg(sp + e);
+            const float4 q = sp[e];
             if (__float_as_int(q.z) == self_peer) continue;
             float dx = xu[0] - q.x, dy = xu[1] - q.y;
             float d2 = dx * dx + dy * dy;
             if (d2 > r2_far) continue;
-            float dist = sqrtf(d2);
-            if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
+            float dist = sqrtf(d2);   // exact in/out-of-radius decision; the unit vector uses one reciprocal (<= 1 ulp)
+            if (!(dist > r) && dist > 0.f) { const float inv = 1.f / dist; gk[0] -= dx * inv; gk[1] -= dy * inv; }
           }
         }
       } else {
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
           float d2 = dx * dx + dy * dy;
           if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
           float dist = sqrtf(d2);
-          if (!(dist > r) && dist > 0.f) { gk[0] -= dx / dist; gk[1] -= dy / dist; }
+          if (!(dist > r) && dist > 0.f) { const float inv = 1.f / dist; gk[0] -= dx * inv; gk[1] -= dy * inv; }
         }
       }
       emit(gk, a.grp.peer_weight);
@@ -304,7 +320,6 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
         for (int d = 0; d < 4; ++d) x[d] = hv[d];
       }
     }
-    __syncthreads();  // s_xu is rewritten next iteration
   }
 
   if (!TAPS) {
@@ -329,8 +344,11 @@ __global__ void __launch_bounds__(1024, 1) ddpm_step_kernel(const StepArgs a) {
 
 static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
   const int threads = args.H * args.spc;
-  size_t smem = sizeof(float4) * (size_t)args.H * args.spc;
+  size_t smem = 2 * sizeof(float4) * (size_t)args.H * args.spc;
   if (args.peers_in_smem) smem += sizeof(float2) * (size_t)args.grp.n_peers * args.H;
+  if (args.hash_in_smem)
+    smem += sizeof(float4) * (size_t)args.grp.n_peers * args.H +
+            sizeof(unsigned short) * (size_t)args.H * (args.grp.peer_grid * args.grp.peer_grid + 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(args.grp.n_groups * args.cpg));
   cfg.blockDim = dim3((unsigned)threads);
@@ -378,18 +396,23 @@ static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
 static int plan_step(StepArgs& a) {
   const int H = a.H, K = a.grp.K;
   if (H < 2 || H > 256 || (H & 1)) return fail(MMDK_EINVAL, "horizon must be even and in [2, 256]");
+  if (H > 512) return fail(MMDK_EINVAL, "horizon too long");
   if (K < 1 || a.grp.n_groups < 1) return fail(MMDK_EINVAL, "n_groups and K must be >= 1");
   if (!a.grp.hard_rows_dev || !a.grp.hard_vals_dev) return fail(MMDK_EINVAL, "hard condition arrays are required");
-  int max_spc = 1024 / H;
+  int max_spc = 512 / H;
   int spc = K < max_spc ? K : max_spc;
   int cpg = (K + spc - 1) / spc;
-  if (cpg > 16) return fail(MMDK_EINVAL, "K too large: a group must fit one thread-block cluster (K <= 16 * floor(1024/H))");
+  if (cpg > 16) return fail(MMDK_EINVAL, "K too large: a group must fit one thread-block cluster (K <= 16 * floor(512/H))");
   // balance the samples over the cluster
   spc = (K + cpg - 1) / cpg;
   a.spc = spc;
   a.cpg = cpg;
   a.peers_in_smem = (a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev == nullptr &&
-                     sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 200 * 1024) ? 1 : 0;
+                     2 * sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 100 * 1024) ? 1 : 0;
+  // two CTAs per SM: stage the hash only while both fit comfortably (<= ~100 KB each)
+  a.hash_in_smem = (a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev != nullptr &&
+                    2 * sizeof(float4) * (size_t)H * spc + sizeof(float4) * (size_t)a.grp.n_peers * H +
+                    sizeof(unsigned short) * (size_t)H * (a.grp.peer_grid * a.grp.peer_grid + 1) <= 100 * 1024) ? 1 : 0;
   if (a.grp.peer_cell_start_dev && (a.grp.peer_grid < 1 || a.grp.peer_grid > MMDK_PEER_GRID_MAX || !a.grp.peer_sorted_dev))
     return fail(MMDK_EINVAL, "peer hash: bad grid size or missing sorted table");
   return MMDK_OK;

@@ -142,7 +142,40 @@ def lower_for_step(guide, n_groups, K, H, device, hard_conds_per_group, constrai
     grp, keep2 = GuideManagerTrajectoriesWithVelocity.lower_groups(
         helper, n_groups, K, H, device, constraints_per_group, hard_conds_per_group, peers, peer_self, peer_radius,
         peer_weight, peer_hash)
-    return env, grp, keep + keep2
+    allk = type(keep2)(list(keep) + list(keep2))
+    allk.rows_d, allk.vals_d = keep2.rows_d, keep2.vals_d
+    return env, grp, allk
+
+
+def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_steps=None, lockstep=False, rep_index=0,
+                     peers_local=None, use_graph=False, keep=None):
+    """One mmdk_run_chain call for a list of reverse steps.  steps: [(t_index, StepScalars)]; noise_steps / chain_steps:
+    contiguous [n_steps, B, H, D] tensors (or None).  Returns the ctypes objects that must stay alive with a captured graph."""
+    lib = _lib.lib()
+    env, grp, _k = lowered
+    n = len(steps)
+    if keep is None:
+        t_arr = (C.c_int * n)(*[int(t) for t, _ in steps])
+        sc_arr = (_lib.StepScalars * n)()
+        for i, (_, sc) in enumerate(steps):
+            sc_arr[i] = sc
+        desc = _lib.ChainDesc()
+        desc.n_steps, desc.t_index, desc.scalars = n, t_arr, sc_arr
+        keep = (desc, t_arr, sc_arr)
+    desc = keep[0]
+    desc.lockstep, desc.rep_index = int(bool(lockstep)), int(rep_index)
+    desc.peers_local_dev = peers_local.data_ptr() if peers_local is not None else None
+    B, H, D = x.shape
+    if noise_steps is not None:
+        assert noise_steps.is_contiguous() and noise_steps.shape[0] >= n and tuple(noise_steps.shape[1:]) == (B, H, D)
+    if chain_steps is not None:
+        assert chain_steps.is_contiguous() and chain_steps.shape[0] >= n and tuple(chain_steps.shape[1:]) == (B, H, D)
+    unet = model.model
+    unet.ensure_time_table(max(t for t, _ in steps) + 1)
+    mode = _lib.UNET_MODES[unet.resolve_precision(model.unet_precision)]
+    _lib.check(lib.mmdk_run_chain(unet.native(), mode, C.byref(env), C.byref(grp), C.byref(desc), H, _lib.ptr(x), _lib.ptr(eps),
+                                  _lib.ptr(noise_steps), _lib.ptr(chain_steps), int(bool(use_graph)), _lib.stream_ptr()))
+    return keep
 
 
 class GaussianDiffusionModel(nn.Module):
@@ -263,14 +296,21 @@ class GaussianDiffusionModel(nn.Module):
         lowered = lower_for_step(guide, 1, B, H, device, [hard_rows],
                                  [guide._own_constraints()] if guide is not None else None)
         eps_buf = torch.empty_like(x)
-        k = 1
+        # noise frames in the reference's draw order (one randn_like per step, sample_functions.py:74), then the whole loop
+        # as ONE native call (mmdk_run_chain)
+        if noise is not None:
+            nz_all = noise[1:1 + n_steps].to(device).to(torch.float32).contiguous()
+        else:
+            nz_all = torch.stack([torch.randn_like(x) for _ in range(n_steps)])
+        steps = []
         for i in reversed(range(-n_diffusion_steps_without_noise, n_diffusion_steps)):
-            nz = noise[k].to(device) if noise is not None else torch.randn_like(x)
             noise_std = 1.0 if noise_std_extra_schedule_fn is None else float(noise_std_extra_schedule_fn(i))
             guided = guide is not None and i < t_start_guide
-            self._fused_step(x, hard_rows, i, guide if guided else None, n_guide_steps, nz, noise_std,
-                             chain[k] if return_chain else None, lowered=lowered, eps_buf=eps_buf, K=B)
-            k += 1
+            sc = self.step_scalars(i, n_guide_steps if guided else 0, noise_std, True)
+            steps.append((max(i, 0), sc))
+        if not self.clip_denoised:
+            raise RuntimeError("clip_denoised=False is rejected by the reference too (diffusion_model_base.py:157)")
+        run_chain_native(self, lowered, steps, x, eps_buf, nz_all, chain[1:] if return_chain else None)
         if return_chain:
             return x, chain.transpose(0, 1)  # [B, steps+1, H, D] like torch.stack(chain, dim=1)
         return x

@@ -28,6 +28,13 @@ def _normalizer_limits(dataset):
     return torch.as_tensor(nz.mins, dtype=torch.float32).cpu(), torch.as_tensor(nz.maxs, dtype=torch.float32).cpu()
 
 
+class KeepList(list):
+    """Device tensors a lowered mmdk_groups points into (kept alive by the caller), with named handles on the ones that may
+    be refreshed in place."""
+    rows_d = None
+    vals_d = None
+
+
 class ConstraintSet:
     """Device arrays of the CostConstraint objects of ONE group, bucketed by waypoint (include/mmdk.h mmdk_groups)."""
 
@@ -194,7 +201,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         """mmdk_groups for `n_groups` planner calls of K samples.  constraints_per_group[g] = (costs, weights);
         hard_conds_per_group[g] = {row: tensor[D]} (normalised) or None."""
         grp = _lib.Groups()
-        keep = []
+        keep = KeepList()
         grp.n_groups, grp.K = n_groups, K
         rows = torch.full((n_groups, _lib.MAX_HARD_ROWS), -1, dtype=torch.int32)
         vals = torch.zeros(n_groups, _lib.MAX_HARD_ROWS, 4, dtype=torch.float32)
@@ -210,6 +217,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
                     vals[g, r] = v[0] if v.dim() == 2 else v
         rows_d, vals_d = rows.to(device), vals.to(device)
         keep += [rows_d, vals_d]
+        keep.rows_d, keep.vals_d = rows_d, vals_d   # refreshed in place by callers that cache the lowering
         grp.hard_rows_dev, grp.hard_vals_dev = rows_d.data_ptr(), vals_d.data_ptr()
         n_obj_total = sum(len(c[0]) for c in constraints_per_group) if constraints_per_group else 0
         if n_obj_total:

@@ -51,7 +51,7 @@ def gather_peers(peers_local: torch.Tensor, n_robots_total: int, group=None) -> 
 class MultiRobotSampler:
     def __init__(self, model: GaussianDiffusionModel, guide, n_guide_steps=20, t_start_guide=None, noise_std=0.5,
                  n_diffusion_steps_without_noise=1, peer_radius=2.4 * 0.05, peer_weight=2e-2, rep_index=0,
-                 process_group=None, use_peer_hash=True):
+                 process_group=None, use_peer_hash=True, use_graph=True):
         self.model, self.guide = model, guide
         self.n_guide_steps = n_guide_steps
         T = model.n_diffusion_steps
@@ -61,6 +61,25 @@ class MultiRobotSampler:
         self.peer_radius, self.peer_weight, self.rep_index = peer_radius, peer_weight, rep_index
         self.pg = process_group
         self.use_peer_hash = use_peer_hash  # False: brute-force scan of the peer table (kept for the equality test)
+        self.use_graph = use_graph          # single-process chains: capture the step loop once, replay (mmdk_run_chain)
+        self._ws = {}
+
+    # -- persistent buffers: stable device pointers let mmdk_run_chain replay its captured CUDA graph -------------------
+    def _workspace(self, key, B, H, D, n_steps, R, R_total, robot_offset, mode, return_chain, dev):
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            ws = dict(x=torch.empty(B, H, D, device=dev), eps=torch.empty(B, H, D, device=dev), noise=None,
+                      chain=torch.empty(n_steps + 1, B, H, D, device=dev) if return_chain else None,
+                      peers=None, peer_self=None, peer_hash=None, lowered=None, keep=None, hc_sig=None)
+            if mode == "lockstep":
+                ws["peers"] = torch.zeros(R_total, H, 2, device=dev)
+                ws["peer_self"] = torch.arange(robot_offset, robot_offset + R, dtype=torch.int32, device=dev)
+                if self.use_peer_hash and R_total > 1:
+                    ws["peer_hash"] = PeerHash(R_total, H, self.peer_radius, dev)
+            self._ws[key] = ws
+        return ws
 
     @torch.no_grad()
     def sample(self, hard_conds_l: Sequence[dict], n_samples: int, noise: Optional[torch.Tensor] = None,
@@ -81,59 +100,98 @@ class MultiRobotSampler:
         distributed = self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                               and n_robots_total is not None and n_robots_total != R)
         R_total = n_robots_total if n_robots_total is not None else R
+        if mode not in ("lockstep", "independent"):
+            raise ValueError("mode must be 'lockstep' or 'independent'")
+        has_constraints = constraints_l is not None and any(len(c[0]) for c in constraints_l)
+        key = (R, K, H, T, n_steps, mode, R_total, robot_offset, bool(return_chain))
+        ws = self._workspace(key, B, H, D, n_steps, R, R_total, robot_offset, mode, return_chain, dev)
+        x, eps, chain = ws["x"], ws["eps"], ws["chain"]
 
+        # ---- inputs into the persistent buffers ---------------------------------------------------------------------
+        step_major = noise is not None and noise.dim() == 4
+        if noise is not None and not step_major:          # robot-major (oracle layout) -> step-major frames
+            noise = noise.to(dev).to(torch.float32).permute(1, 0, 2, 3, 4).reshape(n_steps + 1, B, H, D).contiguous()
         if x_init is not None:
-            x = x_init.reshape(B, H, D).to(torch.float32).clone().contiguous()
+            x.copy_(x_init.reshape(B, H, D))
         elif noise is not None:
-            step_major = noise.dim() == 4
-            x = (noise[0] if step_major else noise[:, 0].reshape(B, H, D)).to(dev).clone().contiguous()
+            x.copy_(noise[0])
         else:
-            x = torch.randn(B, H, D, device=dev, generator=generator)
-        # hard conditions on x_T (diffusion_model_base.py:195)
-        for r, hc in enumerate(hard_conds_l):
-            for row, v in hc.items():
-                x[r * K:(r + 1) * K, row, :] = torch.as_tensor(v, dtype=torch.float32).to(dev)
-        chain = torch.empty(n_steps + 1, B, H, D, device=dev) if return_chain else None
+            x.normal_(generator=generator)
+        if noise is not None:
+            nz_all = noise[1:]
+            nz_all = nz_all if nz_all.is_contiguous() else nz_all.contiguous()
+        else:
+            if ws["noise"] is None:
+                ws["noise"] = torch.empty(n_steps, B, H, D, device=dev)
+            ws["noise"].normal_(generator=generator)      # one draw for the whole chain (the reference: one randn_like per step)
+            nz_all = ws["noise"]
+        # hard conditions on x_T (diffusion_model_base.py:195), vectorised over the robots
+        rows = sorted({int(r) for hc in hard_conds_l for r in hc})
+        if rows:
+            vals = torch.stack([torch.stack([torch.as_tensor(hc[r], dtype=torch.float32).reshape(-1)[:D].to(dev)
+                                             if r in hc else torch.full((D,), float("nan"), device=dev) for r in rows])
+                                for hc in hard_conds_l])                                  # [R, n_rows, D]
+            xv = x.view(R, K, H, D)
+            for j, r in enumerate(rows):
+                v = vals[:, j][:, None, :]
+                xv[:, :, r, :] = torch.where(torch.isnan(v), xv[:, :, r, :], v)
         if return_chain:
             chain[0].copy_(x)
 
-        peers = peer_self = peers_local = peer_hash = None
-        if mode == "lockstep":
-            peers = torch.zeros(R_total, H, 2, device=dev)
-            peers_local = peers[robot_offset:robot_offset + R] if not distributed else torch.zeros(R, H, 2, device=dev)
-            peer_self = torch.arange(robot_offset, robot_offset + R, dtype=torch.int32, device=dev)
-            if self.use_peer_hash and R_total > 1:
-                peer_hash = PeerHash(R_total, H, self.peer_radius, dev)
-        elif mode != "independent":
-            raise ValueError("mode must be 'lockstep' or 'independent'")
+        # ---- lowering (cached while the structure is unchanged; hard-condition VALUES are refreshed in place) ---------
         if constraints_l is None:
             constraints_l = [([], [])] * R
-        env, grp, keep = lower_for_step(guide, R, K, H, dev, list(hard_conds_l), list(constraints_l), peers, peer_self,
-                                        self.peer_radius, self.peer_weight, peer_hash)
-        eps = torch.empty_like(x)
-        k = 1
+        hc_sig = tuple(tuple(sorted(int(r) for r in hc)) for hc in hard_conds_l)
+        if ws["lowered"] is None or has_constraints or ws["hc_sig"] != hc_sig:
+            ws["lowered"] = lower_for_step(guide, R, K, H, dev, list(hard_conds_l), list(constraints_l), ws["peers"],
+                                           ws["peer_self"], self.peer_radius, self.peer_weight, ws["peer_hash"])
+            ws["hc_sig"] = hc_sig
+            ws["keep"] = None
+        else:
+            _refresh_hard_vals(hard_conds_l, ws["lowered"][2].rows_d, ws["lowered"][2].vals_d, H)
+        env, grp, keep = ws["lowered"]
+
+        steps = []
         for i in reversed(range(-self.n_extra, T)):
             guided = guide is not None and i < self.t_start_guide
-            if mode == "lockstep" and guided and R_total > 1:
-                _lib.check(lib.mmdk_publish_peers(C.byref(env), R, K, H, self.rep_index, _lib.ptr(x),
-                                                  _lib.ptr(peers_local), _lib.stream_ptr()))
-                if distributed:
+            steps.append((max(i, 0), model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True), guided))
+
+        lock = mode == "lockstep" and R_total > 1
+        if not (distributed and lock):
+            # one native call for the whole chain (graph replay when the pointers are the persistent ones)
+            from .diffusion import run_chain_native
+            graph_ok = self.use_graph and not has_constraints
+            peers_local = ws["peers"][robot_offset:robot_offset + R] if lock else None
+            ws["keep"] = run_chain_native(model, ws["lowered"], [(t, sc) for t, sc, _ in steps], x, eps, nz_all,
+                                          chain[1:] if return_chain else None, lockstep=lock, rep_index=self.rep_index,
+                                          peers_local=peers_local, use_graph=graph_ok, keep=ws["keep"])
+        else:
+            # fleet sharded over processes: the representative paths are exchanged between publication and hash build
+            peers = ws["peers"]
+            peers_local = torch.zeros(R, H, 2, device=dev)
+            for k, (t, sc, guided) in enumerate(steps):
+                if guided:
+                    _lib.check(lib.mmdk_publish_peers(C.byref(env), R, K, H, self.rep_index, _lib.ptr(x),
+                                                      _lib.ptr(peers_local), _lib.stream_ptr()))
                     peers.copy_(gather_peers(peers_local, R_total, self.pg))
-                if peer_hash is not None:
-                    peer_hash.build(peers)
-            t = max(i, 0)
-            model.model.forward_t(x, t, precision=model.unet_precision, out=eps)
-            sc = model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True)
-            if noise is not None:
-                nz = noise[k] if noise.dim() == 4 else noise[:, k].reshape(B, H, D).to(dev).contiguous()
-            else:
-                nz = torch.randn(B, H, D, device=dev, generator=generator)
-            _lib.check(lib.mmdk_ddpm_step(C.byref(env), C.byref(grp), C.byref(sc), H, _lib.ptr(x), _lib.ptr(eps),
-                                          _lib.ptr(nz), _lib.ptr(chain[k]) if return_chain else None,
-                                          _lib.stream_ptr()))
-            k += 1
-        del keep
-        out = x.reshape(R, K, H, D)
+                    if ws["peer_hash"] is not None:
+                        ws["peer_hash"].build(peers)
+                model.model.forward_t(x, t, precision=model.unet_precision, out=eps)
+                _lib.check(lib.mmdk_ddpm_step(C.byref(env), C.byref(grp), C.byref(sc), H, _lib.ptr(x), _lib.ptr(eps),
+                                              _lib.ptr(nz_all[k]), _lib.ptr(chain[k + 1]) if return_chain else None,
+                                              _lib.stream_ptr()))
+        out = x.reshape(R, K, H, D).clone()
         if return_chain:
-            return out, chain.reshape(n_steps + 1, R, K, H, D).transpose(0, 1)
+            return out, chain.reshape(n_steps + 1, R, K, H, D).transpose(0, 1).clone()
         return out
+
+
+def _refresh_hard_vals(hard_conds_l, rows_d, vals_d, H):
+    """New hard-condition VALUES into the cached lowering (same rows): one stacked copy, no per-robot host sync."""
+    n_g, n_r, D = vals_d.shape
+    cols = []
+    for hc in hard_conds_l:
+        vs = [torch.as_tensor(v, dtype=torch.float32).reshape(-1, D)[0] for v in hc.values()]
+        vs += [torch.zeros(D, dtype=torch.float32, device=vs[0].device if vs else None)] * (n_r - len(vs))
+        cols.append(torch.stack([v.to(vals_d.device, non_blocking=True) for v in vs]))
+    vals_d.copy_(torch.stack(cols))
