@@ -205,17 +205,18 @@ def run_gpu(args):
     hcs_dev = hard_conds_from(sg_host.to(dev))
     kw = dict(mode="lockstep", robot_offset=rank * R_PER_GPU, n_robots_total=R_total)
 
-    # instrument the UNet launches with CUDA events on the launching (current) stream
-    unet_events = []
-    orig_forward_t = unet.forward_t
-
-    def timed_forward_t(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = orig_forward_t(*a, **k)
-        e1.record()
-        unet_events.append((e0, e1))
-        return out
+    # UNet launch durations: the chain is ONE replayed CUDA graph, so host events cannot bracket a forward; the persistent
+    # executor stamps %globaltimer per CTA at start/end of every launch instead (mmdk_unet_debug_stamps); for the other
+    # executors the forwards are timed by a short instrumented pass with CUDA events on the launching stream
+    import ctypes as C
+    from mmd_b200 import _lib
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    STAMP_SLOTS = 256
+    stamps = torch.zeros(STAMP_SLOTS, n_sm, 2, dtype=torch.int64, device=dev)
+    unet.ensure_time_table(T)
+    fused = unet.resolve_precision(args.precision) == "f16x3"
+    if fused:
+        _lib.check(_lib.lib().mmdk_unet_debug_stamps(unet.native(), _lib.ptr(stamps), STAMP_SLOTS, n_sm))
 
     def barrier():
         if world > 1:
@@ -236,16 +237,33 @@ def run_gpu(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    unet.forward_t = timed_forward_t
+    stamps.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         out = sampler.sample(hcs_dev, K, noise=noise, **kw)
     e1.record()
     barrier()
-    unet.forward_t = orig_forward_t
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    unet_ms = [a.elapsed_time(b) for a, b in unet_events]
+    if fused:
+        grid = min((R_PER_GPU * K + 6) // 7, n_sm)
+        st = stamps[:, :grid].cpu()
+        live = (st[:, :, 0] > 0).all(dim=1) & (st[:, :, 1] > 0).all(dim=1)
+        dur_ns = (st[:, :, 1].max(dim=1).values - st[:, :, 0].min(dim=1).values)[live].double()
+        unet_ms = (dur_ns / 1e6).tolist()          # the last replay's forwards (slots are rewritten by every replay)
+        unet_forwards_timed = len(unet_ms)
+    else:
+        xx, oo = torch.randn(R_PER_GPU * K, H, D, device=dev), torch.empty(R_PER_GPU * K, H, D, device=dev)
+        evs = []
+        for i in range(n_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            unet.forward_t(xx, max(T - 1 - i, 0), precision=args.precision, out=oo)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        unet_ms = [a.elapsed_time(b) for a, b in evs]
+        unet_forwards_timed = len(unet_ms)
     unet_avg_ms = sum(unet_ms) / len(unet_ms)
     finite = bool(torch.isfinite(out).all())
 
@@ -275,8 +293,10 @@ def run_gpu(args):
         B = R_PER_GPU * K
         achieved = B * UNET_FLOP_PER_SAMPLE / (unet_avg_ms / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        n_unet_launches = 34 if args.precision == "f16x3" else 1   # pack_input + 33 fused conv layers, or the single fp32 kernel
-        launches_per_chain = n_steps * (n_unet_launches + 1) + (math.ceil(0.5 * T) + N_EXTRA if R_total > 1 else 0)
+        n_unet_launches = 2 if fused else (31 if args.precision == "f16x3_layers" else 1)   # pack_input + persistent forward | pack_input + 30 layer launches | fp32 kernel
+        n_guided = math.ceil(0.5 * T) + N_EXTRA
+        # per reverse step: UNet launches + ddpm_step_kernel; per guided lock-step step: publish_peers + build_peer_hash
+        launches_per_chain = n_steps * (n_unet_launches + 1) + (2 * n_guided if R_total > 1 else 0)
         cb_v, tu, tg, per_robot = (None, None, None, None)
         cores = os.cpu_count() or 1
         cpu = None
@@ -295,12 +315,16 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(sg_host.numel() * 4), "d2h_bytes_per_step": int(result_host.numel() * 4),
                     "note": "noise drawn on the device by torch.randn as the reference does"},
             "gpu_launches": launches_per_chain * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "TemporalUnet forward (" + args.precision + (": pack_input + 33 conv_tc_kernel launches)" if args.precision == "f16x3" else ": unet_ffma_kernel)"), "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "TemporalUnet forward (" + args.precision + (": unet_fused_kernel, one persistent tcgen05 launch)" if fused else ")"), "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                         f"dense TF32 is nominally half of it",
                          "algorithmic_flop_per_launch": B * UNET_FLOP_PER_SAMPLE, "avg_launch_ms": unet_avg_ms,
-                         "unet_share_of_step": sum(unet_ms) / ms_total},
+                         "unet_share_of_step": unet_avg_ms * n_steps / ms_step,
+                         "timing": ("%globaltimer stamps written by every CTA of every forward of the last timed chain (the chain is one "
+                                    "replayed CUDA graph): max(end) - min(start) per launch" if fused else
+                                    "CUDA events around every forward of an instrumented pass on the launching stream"),
+                         "forwards_timed": unet_forwards_timed},
             "cpu_baseline": cpu, "clocks": clk,
         }
         print(json.dumps(line))
@@ -314,7 +338,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mmd_b200", choices=["mmd_b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MMD_UNET_PRECISION", "f16x3"), choices=["fp32", "f16x3"])
+    ap.add_argument("--precision", default=os.environ.get("MMD_UNET_PRECISION", "f16x3"), choices=["fp32", "f16x3", "f16x3_layers"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -94,6 +94,12 @@ int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int*
  * issuer waited for weights, 7 epilogue idle since); dbg_dev = NULL switches it off. */
 int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_dev, void* stream);
 
+/* Launch-duration probe of the persistent executor (bench.py's roofline: works inside replayed CUDA graphs, where host
+ * events cannot be placed): from the next MMDK_UNET_F16X3 forward on, every CTA writes its first and last %globaltimer
+ * reading (ns) into stamps_dev [n_slots, max_ctas, 2] uint64; forward number i (counted from this call, or baked at capture
+ * time) uses slot i mod n_slots.  Launch duration = max(end) - min(start) over the CTAs of a slot.  NULL switches it off. */
+int mmdk_unet_debug_stamps(const mmdk_unet* net, unsigned long long* stamps_dev, int n_slots, int max_ctas);
+
 /* Calibration (profiles/): n_ctas CTAs each issue n_iters back-to-back tcgen05.mma (M=128, N, K=16, kind::f16, SS mode)
  * rotating over n_acc (1, 2 or 4) TMEM accumulators, and write {elapsed clock64 cycles, n_iters} to out_dev
  * [n_ctas, 2] int64.  Run under ncu to read what sm__pipe_tensor_cycles_active reports for a loop that is 100% MMA. */

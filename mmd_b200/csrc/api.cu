@@ -100,6 +100,16 @@ int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_
   return unet_tc_timeline(net->impl, op_index, dbg_dev, (cudaStream_t)stream);
 }
 
+int mmdk_unet_debug_stamps(const mmdk_unet* net, unsigned long long* stamps_dev, int n_slots, int max_ctas) {
+  if (!net) return fail(MMDK_EINVAL, "null argument");
+  if (stamps_dev && (n_slots < 1 || max_ctas < 1)) return fail(MMDK_EINVAL, "stamps: n_slots and max_ctas must be >= 1");
+  net->impl->stamps = stamps_dev;
+  net->impl->stamp_slots = stamps_dev ? n_slots : 0;
+  net->impl->stamp_ctas = stamps_dev ? max_ctas : 0;
+  net->impl->stamp_next = 0;
+  return MMDK_OK;
+}
+
 int mmdk_debug_mma_calibrate(int N, int n_iters, int n_ctas, int n_acc, long long* out_dev, void* stream) {
   if (!out_dev) return fail(MMDK_EINVAL, "null argument");
   return mma_calibrate(N, n_iters, n_ctas, n_acc, out_dev, (cudaStream_t)stream);

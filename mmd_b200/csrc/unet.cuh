@@ -25,6 +25,9 @@ struct UnetImpl {
   FusedState* fused_last = nullptr;
   int last_mode = 0;
   long long* fused_dbg = nullptr;   // debug timeline buffer of the fused executor (mmdk_unet_debug_timeline)
+  unsigned long long* stamps = nullptr;   // launch-duration probe of the fused executor (mmdk_unet_debug_stamps)
+  int stamp_slots = 0, stamp_ctas = 0;
+  unsigned stamp_next = 0;
 };
 
 int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names, const float* const* tensors,

@@ -99,6 +99,7 @@ struct FParams {
   uint32_t off_ring, off_prm, off_part, off_stat, off_bar;
   int dbg_flags;              // timing experiments only (MMDK_FUSED_DEBUG): 1 = no weight copies after the first ring fill, 2 = hi*hi term only
   long long* dbg;             // optional timeline of CTA 0: [item][16] clock64 stamps (see tests/tc_timeline.py), nullptr in production
+  unsigned long long* stamp;  // optional launch-duration probe: [grid][2] %globaltimer (ns) at CTA start / end (mmdk_unet_debug_stamps)
   FOp ops[F_MAX_OPS];
   FChunk chunks[F_MAX_CHUNKS];
 };
@@ -109,6 +110,11 @@ constexpr int B_IN_FULL = 0, B_IN_EMPTY = 2, B_ACC_FULL = 4, B_ACC_EMPTY = 6, B_
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
 #define FSTAMP(item, slot) do { if (P.dbg && blockIdx.x == 0) P.dbg[(size_t)(item) * 16 + (slot)] = clock64(); } while (0)
 
   if (tid == 0) {
+    if (P.stamp) P.stamp[2 * blockIdx.x] = globaltimer_ns();
     for (int i = 0; i < 2; ++i) {
       mbar_init(FBAR(B_IN_FULL + i), 1);
       mbar_init(FBAR(B_IN_EMPTY + i), 1);
@@ -589,6 +596,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (P.stamp && tid == 0) P.stamp[2 * blockIdx.x + 1] = globaltimer_ns();
   if (warp == F_WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -894,6 +902,11 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
   P.cond_row = net->cond_table + (size_t)t * net->n_cond;
   P.eps = eps;
   P.dbg = net->fused_dbg;
+  P.stamp = nullptr;
+  if (net->stamps && net->stamp_slots > 0 && st->grid <= net->stamp_ctas) {
+    // slot chosen at launch (= capture) time: a replayed graph keeps rewriting the slots of its own forwards
+    P.stamp = net->stamps + (size_t)(net->stamp_next++ % net->stamp_slots) * net->stamp_ctas * 2;
+  }
   { const char* e = getenv("MMDK_FUSED_DEBUG"); P.dbg_flags = e ? atoi(e) : 0; }
   unet_fused_kernel<<<st->grid, F_THREADS, st->smem, stream>>>(P);
   return check_cuda(cudaGetLastError(), "unet_fused_kernel launch");
