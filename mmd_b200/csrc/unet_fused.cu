@@ -130,14 +130,71 @@ __device__ __forceinline__ uint4 ld_cg_u4(const void* p) { return __ldcg(reinter
 
 struct EpiCtx {
   int tid, warp, lane, q4, cb, row;
-  float4* prm4;      // [N] (bias, gamma, beta, cond) of this item
-  float* prm_rb;     // [N] residual-conv bias
+  // per-channel parameters of this item, structure of arrays (each [F_MAX_N] floats): one LDS.128 serves 4 channels
+  float* p_bias;
+  float* p_gamma;
+  float* p_beta;
+  float* p_cond;
+  float* p_rb;       // residual-conv bias
   float2* part;      // [8][F_PART_ROWS] (sum, M2) per group and image row
-  float2* stat;      // [ST * 8] (mean, rstd) of this item
+  float2* stat;      // [ST * 8] (-mean * rstd, rstd) of this item
   uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
   int tile, img, B;
   long long* dbg;    // this item's stamp row (CTA 0, thread 0 only) or nullptr
 };
+
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: two lanes per issue slot) and approx transcendental wrappers -----
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Mish on two values: y * tanh(softplus(y)) = y * n / (n + 2), n = e^y (e^y + 2); for y >= 20 the ratio is exactly 1 in
+// fp32, so clamping the exponent's argument replaces the overflow guard
+__device__ __forceinline__ float2 mish2(float2 y) {
+  const float2 t = f2mul(make_float2(fminf(y.x, 20.f), fminf(y.y, 20.f)), make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 e = make_float2(ex2_ftz(t.x), ex2_ftz(t.y));
+  const float2 n = f2mul(e, f2add(e, make_float2(2.f, 2.f)));
+  const float2 d = f2add(n, make_float2(2.f, 2.f));
+  const float2 r = make_float2(rcp_ftz(d.x), rcp_ftz(d.y));
+  return f2mul(y, f2mul(n, r));
+}
+
+// 8 fp32 (as 4 float2) -> 8 fp16 hi (uint4) + 8 fp16 lo (uint4)
+__device__ __forceinline__ void split8p(const float2* y, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __float22half2_rn(y[i]);
+    const float2 back = __half22float2(hh);
+    const float2 rem = f2add(y[i], make_float2(-back.x, -back.y));
+    const __half2 ll = __float22half2_rn(rem);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void add8p(const uint4& hi, const uint4& lo, float2* y) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = f2add(y[i], f2add(__half22float2(h[i]), __half22float2(l[i])));
+}
 
 // Conv1dBlock epilogue (+cond, +residual image), NMT m-tiles of N columns.
 template <int NMT, int N>
@@ -162,14 +219,16 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
       uint8_t* obase = op->out2 + (size_t)c.img * op->out2_tile_bytes + (size_t)(2 + q) * 16;
 #pragma unroll 1
       for (int pc = 0; pc < NP; ++pc) {
-        float y[8];
-        tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, y);
+        float2 y[4];
+        tmem_ld8(lane_base + 128 + i * N + c0 + pc * 8, reinterpret_cast<float*>(y));
         tmem_wait_ld();
         if (ok) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] += c.prm_rb[c0 + pc * 8 + e];
+          const float4 b0 = *reinterpret_cast<const float4*>(c.p_rb + c0 + pc * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(c.p_rb + c0 + pc * 8 + 4);
+          y[0] = f2add(y[0], make_float2(b0.x, b0.y)); y[1] = f2add(y[1], make_float2(b0.z, b0.w));
+          y[2] = f2add(y[2], make_float2(b1.x, b1.y)); y[3] = f2add(y[3], make_float2(b1.z, b1.w));
           uint4 hi, lo;
-          split8(y, hi, lo);
+          split8p(y, hi, lo);
           uint8_t* ob = obase + (size_t)((c0 >> 3) + pc) * op->out2_rows * 16;
           *reinterpret_cast<uint4*>(ob) = hi;
           *reinterpret_cast<uint4*>(ob + oplane) = lo;
@@ -178,9 +237,9 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     }
   }
   // ---- accumulators -> registers, TMEM released ---------------------------------------------------------------------
-  float v[NMT][NH];
+  float2 v[NMT][NH / 2];
 #pragma unroll
-  for (int i = 0; i < NMT; ++i) tmem_ldn<NH>(lane_base + i * N + c0, v[i]);
+  for (int i = 0; i < NMT; ++i) tmem_ldn<NH>(lane_base + i * N + c0, reinterpret_cast<float*>(v[i]));
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
@@ -206,61 +265,84 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     rl = ld_cg_u4(rimg + (size_t)(2 + c.row) * 16 + rplane);
   }
 
-  // ---- + bias, per-row (sum, M2) of both groups ----------------------------------------------------------------------
+  // ---- + bias, per-row (sum, M2) of both groups (packed adds; the bias of 4 channels per LDS.128) ----------------------
+  {
+    float2 b2[NH / 2];
 #pragma unroll
-  for (int i = 0; i < NMT; ++i) {
+    for (int k = 0; k < NH / 4; ++k) {
+      const float4 bq = *reinterpret_cast<const float4*>(c.p_bias + c0 + 4 * k);
+      b2[2 * k] = make_float2(bq.x, bq.y);
+      b2[2 * k + 1] = make_float2(bq.z, bq.w);
+    }
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      float sm = 0.f;
+    for (int i = 0; i < NMT; ++i) {
 #pragma unroll
-      for (int k = 0; k < CPG; ++k) {
-        const float t = v[i][g * CPG + k] + c.prm4[c0 + g * CPG + k].x;
-        v[i][g * CPG + k] = t;
-        sm += t;
+      for (int g = 0; g < 2; ++g) {
+        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CPG / 2; ++k) {
+          const float2 t = f2add(v[i][g * (CPG / 2) + k], b2[g * (CPG / 2) + k]);
+          v[i][g * (CPG / 2) + k] = t;
+          s2 = f2add(s2, t);
+        }
+        const float sm = s2.x + s2.y;
+        const float nm = sm * (-1.f / CPG);
+        const float2 nm2 = make_float2(nm, nm);
+        float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CPG / 2; ++k) {
+          const float2 d = f2add(v[i][g * (CPG / 2) + k], nm2);
+          q2 = f2fma(d, d, q2);
+        }
+        c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, q2.x + q2.y);
       }
-      const float m = sm * (1.f / CPG);
-      float m2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < CPG; ++k) { const float d = v[i][g * CPG + k] - m; m2 = fmaf(d, d, m2); }
-      c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, m2);
     }
   }
   if (c.dbg) c.dbg[9] = clock64();
   epi_bar16();
   if (c.dbg) c.dbg[10] = clock64();
-  // ---- Chan combination: 8 threads per (sample, group) ----------------------------------------------------------------
+  // ---- Chan combination: 8 threads per (sample, group), partials read ONCE into registers --------------------------------
   if (c.tid < ST * 8 * 8) {
     const int pair = c.tid >> 3, sub = c.tid & 7;
     const int s = pair >> 3, g = pair & 7;
     const float2* pg = c.part + g * F_PART_ROWS + s * Pp;
     const float inv_n = 1.f / (float)(CPG * L);
+    float2 e[8];                       // L <= 64 (checked by the host)
     float sum = 0.f;
-    for (int pp = sub; pp < L; pp += 8) sum += pg[pp].x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pp = sub + 8 * j;
+      e[j] = (pp < L) ? pg[pp] : make_float2(0.f, 0.f);
+      sum += e[j].x;
+    }
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     sum += __shfl_xor_sync(0xffffffffu, sum, 4);
     const float mean = sum * inv_n;
     float m2 = 0.f;
-    for (int pp = sub; pp < L; pp += 8) {
-      const float2 e = pg[pp];
-      const float d = e.x * (1.f / CPG) - mean;
-      m2 += e.y + (float)CPG * d * d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = e[j].x * (1.f / CPG) - mean;
+      m2 += (sub + 8 * j < L) ? e[j].y + (float)CPG * d * d : 0.f;
     }
     m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
     m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
     m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
-    if (sub == 0) c.stat[pair] = make_float2(mean, rsqrtf(m2 * inv_n + 1e-5f));
+    if (sub == 0) {
+      const float rstd = rsqrtf(m2 * inv_n + 1e-5f);
+      c.stat[pair] = make_float2(-mean * rstd, rstd);
+    }
   }
   epi_bar16();
   if (c.dbg) c.dbg[11] = clock64();
-  // ---- normalise, Mish, +cond, +residual image, split, store: one flat sequence of (m-tile, panel) steps with the
-  // residual of the NEXT step already in flight ------------------------------------------------------------------------
+  // ---- normalise, Mish, +cond, +residual image, split, store: one flat sequence of (panel, m-tile) steps -- the per-channel
+  // parameters of a panel are loaded once for all m-tiles -- with the residual of the NEXT step already in flight ------------
 #pragma unroll
   for (int step = 0; step < NMT * NP; ++step) {
-    const int i = step / NP, pc = step % NP;
+    const int pc = step / NMT, i = step % NMT;
     const uint4 ch = rh, cl = rl;
     if (step + 1 < NMT * NP) {
-      const int i2 = (step + 1) / NP, pc2 = (step + 1) % NP;
+      const int pc2 = (step + 1) / NMT, i2 = (step + 1) % NMT;
       if (rimg && okv[i2]) {
         const uint8_t* rp = rimg + (size_t)(2 + 128 * i2 + c.row) * 16 + (size_t)pc2 * op->res_id_rows * 16;
         rh = ld_cg_u4(rp);
@@ -269,20 +351,25 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     }
     if (okv[i]) {
       const int si = siv[i];
+      const float4 ga = *reinterpret_cast<const float4*>(c.p_gamma + c0 + pc * 8), gb = *reinterpret_cast<const float4*>(c.p_gamma + c0 + pc * 8 + 4);
+      const float4 ba = *reinterpret_cast<const float4*>(c.p_beta + c0 + pc * 8), bb = *reinterpret_cast<const float4*>(c.p_beta + c0 + pc * 8 + 4);
+      const float4 ca = *reinterpret_cast<const float4*>(c.p_cond + c0 + pc * 8), cbv = *reinterpret_cast<const float4*>(c.p_cond + c0 + pc * 8 + 4);
+      const float2 gam[4] = {make_float2(ga.x, ga.y), make_float2(ga.z, ga.w), make_float2(gb.x, gb.y), make_float2(gb.z, gb.w)};
+      const float2 bet[4] = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w), make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
+      const float2 cnd[4] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cbv.x, cbv.y), make_float2(cbv.z, cbv.w)};
       const float2 st0 = c.stat[si * 8 + c.cb * 2], st1 = c.stat[si * 8 + c.cb * 2 + 1];
-      float y[8];
+      float2 y[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = pc * 8 + e;
+      for (int e = 0; e < 4; ++e) {
+        const int k = pc * 8 + 2 * e;                   // first of the two channels (both in the same group: CPG is even)
         const float2 st = (k < CPG) ? st0 : st1;
-        const float4 pr = c.prm4[c0 + k];
-        float t = (v[i][k] - st.x) * st.y;
-        t = fmaf(t, pr.y, pr.z);
-        y[e] = mish_fast(t) + pr.w;
+        float2 t = f2fma(v[i][pc * 4 + e], make_float2(st.y, st.y), make_float2(st.x, st.x));
+        t = f2fma(t, gam[e], bet[e]);
+        y[e] = f2add(mish2(t), cnd[e]);
       }
-      if (rimg) add8(ch, cl, y);
+      if (rimg) add8p(ch, cl, y);
       uint4 hi, lo;
-      split8(y, hi, lo);
+      split8p(y, hi, lo);
       uint8_t* ob = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)(2 + 128 * i + c.row) * 16 +
                     (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
       *reinterpret_cast<uint4*>(ob) = hi;
@@ -310,7 +397,7 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
         if (ok) {
           const size_t b = (size_t)c.tile * ST + si;
           *reinterpret_cast<float4*>(eps + (b * L + pi) * 4) =
-              make_float4(y[0] + c.prm4[0].x, y[1] + c.prm4[1].x, y[2] + c.prm4[2].x, y[3] + c.prm4[3].x);
+              make_float4(y[0] + c.p_bias[0], y[1] + c.p_bias[1], y[2] + c.p_bias[2], y[3] + c.p_bias[3]);
         }
       }
     }
@@ -342,7 +429,7 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
           tmem_wait_ld();
           if (ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] += c.prm4[cbase + e].x;
+            for (int e = 0; e < 8; ++e) y[e] += c.p_bias[cbase + e];
             uint4 hi, lo;
             split8(y, hi, lo);
             uint8_t* ob = obase + (size_t)(cbase / 8) * op->out_rows * 16;
@@ -554,8 +641,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       const int p = k & 1;
       c.tile = (int)blockIdx.x + (2 * r_ + par) * G;
       c.img = P.by_slot ? (int)blockIdx.x * 2 + par : c.tile;
-      c.prm4 = reinterpret_cast<float4*>(smem + P.off_prm + (uint32_t)p * (F_MAX_N * 20));
-      c.prm_rb = reinterpret_cast<float*>(c.prm4 + F_MAX_N);
+      c.p_bias = reinterpret_cast<float*>(smem + P.off_prm + (uint32_t)p * (F_MAX_N * 20));
+      c.p_gamma = c.p_bias + F_MAX_N;
+      c.p_beta = c.p_bias + 2 * F_MAX_N;
+      c.p_cond = c.p_bias + 3 * F_MAX_N;
+      c.p_rb = c.p_bias + 4 * F_MAX_N;
       c.stat = reinterpret_cast<float2*>(smem + P.off_stat + (uint32_t)p * 512);
       c.tmem = tmem_base + (uint32_t)p * 256u;
       c.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg + (size_t)k * 16 : nullptr;
@@ -564,9 +654,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       const int N = op->N;
       if (tid < N) {
         const float* cond = (op->cond_off >= 0) ? P.cond_row + op->cond_off : nullptr;
-        c.prm4[tid] = make_float4((tid < op->cout) ? __ldg(op->bias + tid) : 0.f, op->gamma ? __ldg(op->gamma + tid) : 1.f,
-                                  op->beta ? __ldg(op->beta + tid) : 0.f, cond ? __ldg(cond + tid) : 0.f);
-        c.prm_rb[tid] = op->res_bias ? __ldg(op->res_bias + tid) : 0.f;
+        c.p_bias[tid] = (tid < op->cout) ? __ldg(op->bias + tid) : 0.f;
+        c.p_gamma[tid] = op->gamma ? __ldg(op->gamma + tid) : 1.f;
+        c.p_beta[tid] = op->beta ? __ldg(op->beta + tid) : 0.f;
+        c.p_cond[tid] = cond ? __ldg(cond + tid) : 0.f;
+        c.p_rb[tid] = op->res_bias ? __ldg(op->res_bias + tid) : 0.f;
       }
       epi_bar16();
       mbar_wait(FBAR(B_ACC_FULL + p), (uint32_t)((p ? nuse1 : nuse0) & 1));
@@ -692,6 +784,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
     p.variant = FV_GENERIC;
     if (p.kind == TC_CONVBLOCK) {
       if (op.n_groups != 8) return fail_free("tensor-core executor: GroupNorm needs 8 groups");
+      if (op.lin > 64) return fail_free("tensor-core executor: horizon > 64 not supported");
       if (p.n_mt == 4 && p.N == 32) p.variant = FV_4_32;
       else if (p.n_mt == 2 && p.N == 64) p.variant = FV_2_64;
       else if (p.n_mt == 1 && p.N == 128) p.variant = FV_1_128;
