@@ -87,6 +87,11 @@ int mmdk_unet_cond_row(const mmdk_unet* net, int t, float* out_dev, int* n_cond,
 int mmdk_unet_debug_tap(const mmdk_unet* net, int op_index, float* out_dev, int* c_out, int* l_out, int* n_ops_out,
                         void* stream);
 
+/* Debug: the persistent executor (MMDK_UNET_F16X3) hands most activations from one op to the next inside shared memory and
+ * never writes them to global memory; on != 0 makes every later forward also store every activation image so that
+ * mmdk_unet_debug_tap can read it (same arithmetic, same eps).  Off by default. */
+int mmdk_unet_debug_keep_activations(const mmdk_unet* net, int on);
+
 /* Debug: from the next MMDK_UNET_F16X3 forward on, op `op_index` writes a per-CTA clock64 timeline into
  * dbg_dev [n_tiles, 16] int64 (slot 15 = SM id); op_index = -1 / dbg_dev = NULL switches it off (per-layer executor).
  * op_index = -2: the persistent executor (MMDK_UNET_F16X3) writes CTA 0's per-item stamps [n_items, 16] int64 into dbg_dev

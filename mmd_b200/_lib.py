@@ -57,7 +57,7 @@ class ChainDesc(C.Structure):
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
-    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_unet_debug_stamps", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
+    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_unet_debug_stamps", "mmdk_unet_debug_keep_activations", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize", "mmdk_get_conflicts", "mmdk_smooth_trajs",
 ]
 
@@ -88,6 +88,7 @@ def load():
     lib.mmdk_unet_cond_row.argtypes = [vp, i, vp, c_int_p, vp]
     lib.mmdk_unet_debug_tap.argtypes = [vp, i, vp, c_int_p, c_int_p, c_int_p, vp]
     lib.mmdk_unet_debug_timeline.argtypes = [vp, i, vp, vp]
+    lib.mmdk_unet_debug_keep_activations.argtypes = [vp, i]
     lib.mmdk_unet_debug_stamps.argtypes = [vp, vp, i, i]
     lib.mmdk_debug_mma_calibrate.argtypes = [i, i, i, i, vp, vp]
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]

@@ -100,6 +100,12 @@ int mmdk_unet_debug_timeline(const mmdk_unet* net, int op_index, long long* dbg_
   return unet_tc_timeline(net->impl, op_index, dbg_dev, (cudaStream_t)stream);
 }
 
+int mmdk_unet_debug_keep_activations(const mmdk_unet* net, int on) {
+  if (!net) return fail(MMDK_EINVAL, "null argument");
+  net->impl->fused_keep = on != 0;
+  return MMDK_OK;
+}
+
 int mmdk_unet_debug_stamps(const mmdk_unet* net, unsigned long long* stamps_dev, int n_slots, int max_ctas) {
   if (!net) return fail(MMDK_EINVAL, "null argument");
   if (stamps_dev && (n_slots < 1 || max_ctas < 1)) return fail(MMDK_EINVAL, "stamps: n_slots and max_ctas must be >= 1");

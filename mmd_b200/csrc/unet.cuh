@@ -24,6 +24,7 @@ struct UnetImpl {
   std::map<int, FusedState*> fused;   // per batch size (bounded; see unet_forward_fused)
   FusedState* fused_last = nullptr;
   int last_mode = 0;
+  bool fused_keep = false;          // fused executor writes every activation image to global memory (mmdk_unet_debug_keep_activations)
   long long* fused_dbg = nullptr;   // debug timeline buffer of the fused executor (mmdk_unet_debug_timeline)
   unsigned long long* stamps = nullptr;   // launch-duration probe of the fused executor (mmdk_unet_debug_stamps)
   int stamp_slots = 0, stamp_ctas = 0;

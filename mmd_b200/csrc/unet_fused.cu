@@ -74,6 +74,12 @@ struct FOp {
   uint8_t* out2;
   uint32_t out2_tile_bytes;
   int out2_rows, out2_C;
+  // in-place activation hand-over inside shared memory: this op's epilogue writes its output image straight into the tile's
+  // (now free) input buffer, where the next op of the same tile reads it as its A operand -- no L2 round trip on the tile's
+  // critical path; the global image is written only when a later op needs it (identity residual, skip concat, debug taps)
+  int in_smem;      // input already in the parity's buffer (placed by the previous op's epilogue): the producer copies nothing
+  int out_smem;     // write the output image into the parity's buffer
+  int out_global;   // write the output image to global memory
 };
 
 // weight chunk, 16 bytes (one uniform constant load per chunk); everything the MMA issuer needs is precomputed on the host
@@ -117,6 +123,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar16() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <int NH>
@@ -139,6 +146,7 @@ struct EpiCtx {
   float2* part;      // [8][F_PART_ROWS] (sum, M2) per group and image row
   float2* stat;      // [ST * 8] (-mean * rstd, rstd) of this item
   uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
+  uint8_t* sbuf;     // the parity's input buffer (shared memory), target of the in-place output
   int tile, img, B;
   long long* dbg;    // this item's stamp row (CTA 0, thread 0 only) or nullptr
 };
@@ -335,6 +343,15 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
   }
   epi_bar16();
   if (c.dbg) c.dbg[11] = clock64();
+  const bool out_smem = op->out_smem != 0, out_global = op->out_global != 0;
+  if (out_smem) {   // the two rows above and below the m-tiles (conv halos of the first / last sample)
+    const int n_pan = op->out_C / 4;   // hi + lo panels
+    if (c.tid < n_pan * 4) {
+      const int pan = c.tid >> 2, e = c.tid & 3;
+      const int r = (e < 2) ? e : op->out_rows - 4 + e;
+      *reinterpret_cast<uint4*>(c.sbuf + ((size_t)pan * op->out_rows + r) * 16) = make_uint4(0, 0, 0, 0);
+    }
+  }
   // ---- normalise, Mish, +cond, +residual image, split, store: one flat sequence of (panel, m-tile) steps -- the per-channel
   // parameters of a panel are loaded once for all m-tiles -- with the residual of the NEXT step already in flight ------------
 #pragma unroll
@@ -349,6 +366,7 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
         rl = ld_cg_u4(rp + rplane);
       }
     }
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
     if (okv[i]) {
       const int si = siv[i];
       const float4 ga = *reinterpret_cast<const float4*>(c.p_gamma + c0 + pc * 8), gb = *reinterpret_cast<const float4*>(c.p_gamma + c0 + pc * 8 + 4);
@@ -368,12 +386,17 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
         y[e] = f2add(mish2(t), cnd[e]);
       }
       if (rimg) add8p(ch, cl, y);
-      uint4 hi, lo;
       split8p(y, hi, lo);
-      uint8_t* ob = op->out + (size_t)c.img * op->out_tile_bytes + (size_t)(2 + 128 * i + c.row) * 16 +
-                    (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
+    }
+    const size_t ooff = (size_t)(2 + 128 * i + c.row) * 16 + (size_t)((c0 >> 3) + pc) * op->out_rows * 16;
+    if (okv[i] && out_global) {
+      uint8_t* ob = op->out + (size_t)c.img * op->out_tile_bytes + ooff;
       *reinterpret_cast<uint4*>(ob) = hi;
       *reinterpret_cast<uint4*>(ob + oplane) = lo;
+    }
+    if (out_smem) {   // every image row of the m-tiles is written: rows outside a sample (conv halos, unused samples) as zeros
+      *reinterpret_cast<uint4*>(c.sbuf + ooff) = hi;
+      *reinterpret_cast<uint4*>(c.sbuf + ooff + oplane) = lo;
     }
   }
   if (c.dbg) c.dbg[12] = clock64();
@@ -504,9 +527,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
         FSTAMP(k, 0);
         const uint32_t base = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
         uint32_t total = 0;
-        const int ns = op->n_src;
+        const int ns = op->in_smem ? 0 : op->n_src;
         for (int s = 0; s < ns; ++s) total += op->src_tile_bytes[s];
-        mbar_expect_tx(FBAR(B_IN_FULL + p), total);
+        if (op->in_smem) mbar_arrive(FBAR(B_IN_FULL + p));   // the previous op's epilogue left the image in the buffer
+        else mbar_expect_tx(FBAR(B_IN_FULL + p), total);
         for (int s = 0; s < ns; ++s) {
           const uint32_t tb = op->src_tile_bytes[s];
           const uint8_t* g = op->src[s] + (size_t)(op->src_by_tile[s] ? tile : slot) * tb;
@@ -648,6 +672,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       c.p_rb = c.p_bias + 4 * F_MAX_N;
       c.stat = reinterpret_cast<float2*>(smem + P.off_stat + (uint32_t)p * 512);
       c.tmem = tmem_base + (uint32_t)p * 256u;
+      // in-place hand-over target = the buffer the NEXT op of this tile will use: items alternate buffers, so it is this
+      // item's own (free) buffer while the round has two tiles, and the other buffer in a single-tile round
+      c.sbuf = smem + (size_t)((2 * r_ + 1 < n_my) ? p : (p ^ 1)) * P.buf_bytes;
       c.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg + (size_t)k * 16 : nullptr;
       if (tid == 0) FSTAMP(k, 7);
       // per-channel parameters of this op while its MMAs run
@@ -676,8 +703,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       } else {
         epi_plain(op, c, bae, P.eps);
       }
-      // output image visible to the async proxy (the input producer's bulk copies) before the arrival
+      // output image visible to the async proxy (the input producer's bulk copies / the next op's MMAs) before the arrival
       fence_proxy_async_global();
+      if (op->out_smem) fence_proxy_async_smem();
       if (c.dbg) c.dbg[13] = clock64();
       __syncwarp();
       if (lane == 0) mbar_arrive(FBAR(B_OUT_DONE + par));
@@ -705,6 +733,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------------------------
 struct FusedState {
   int B = 0, n_tiles = 0, grid = 0, by_slot = 0;
+  bool keep_all = false;           // every activation image also goes to global memory (debug taps)
   std::vector<TcImage> images;     // [0] = packed network input, [1 + j] = output of op j
   std::vector<TcImage> images_r;   // [j] = residual-conv image written by op j (dev == nullptr if none)
   std::vector<uint8_t*> owned;     // distinct device allocations behind the images (buffers may be shared)
@@ -728,7 +757,7 @@ void unet_fused_release(UnetImpl* net) {
   net->fused.clear();
 }
 
-static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, FusedState** out) {
+static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStream_t stream, FusedState** out) {
   const auto& cfg = net->cfg;
   if (cfg.self_attention) return fail(MMDK_EINVAL, "tensor-core executor: LinearAttention not supported");
   if (cfg.state_dim > 8) return fail(MMDK_EINVAL, "tensor-core executor: state_dim > 8 not supported");
@@ -741,6 +770,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
   st->n_tiles = (B + ST - 1) / ST;
   st->grid = std::min(st->n_tiles, n_sm);
   st->by_slot = by_slot;
+  st->keep_all = keep_all;
   const int n_img = by_slot ? 2 * st->grid : st->n_tiles;   // entries of every intermediate image
   const int n_ops = (int)net->ops.size();
   st->images.resize(n_ops + 1);
@@ -927,6 +957,28 @@ static int build_fused(UnetImpl* net, int B, int by_slot, cudaStream_t stream, F
   }
   if (2 * buf > avail) return fail_free("tensor-core executor: an op's input images do not fit in shared memory");
   for (int j = 0; j < n_ops; ++j) st->ops[j].big = in_bytes[j] > buf ? 1 : 0;
+  // in-place hand-over (see FOp): conv block j -> op j + 1 when j + 1 reads nothing but j's output at the same resolution
+  for (int j = 0; j < n_ops; ++j) { st->ops[j].in_smem = 0; st->ops[j].out_smem = 0; st->ops[j].out_global = 1; }
+  const bool inplace_on = getenv("MMDK_FUSED_NO_INPLACE") == nullptr;
+  for (int j = 0; inplace_on && j + 1 < n_ops; ++j) {
+    FOp& a = st->ops[j];
+    FOp& b = st->ops[j + 1];
+    if (a.kind != TC_CONVBLOCK || a.big || b.big || b.n_src != 1 || b.src[0] != a.out || b.L != a.out_L) continue;
+    if (a.out_tile_bytes > buf || b.src_smem_off[0] != 0) continue;
+    a.out_smem = 1;
+    b.in_smem = 1;
+  }
+  for (int j = 0; j < n_ops; ++j) {
+    FOp& a = st->ops[j];
+    if (a.kind == TC_FINAL || !a.out) continue;
+    bool needed = keep_all;
+    for (int m = j + 1; m < n_ops && !needed; ++m) {
+      const FOp& b = st->ops[m];
+      if (b.res_id == a.out) needed = true;
+      if (!b.in_smem) for (int k = 0; k < b.n_src; ++k) if (b.src[k] == a.out) needed = true;
+    }
+    a.out_global = needed ? 1 : 0;
+  }
   FParams& P = st->prm;
   P.buf_bytes = buf;
   P.off_ring = 2 * buf;
@@ -959,6 +1011,11 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
   FusedState* st = nullptr;
   auto it = net->fused.find(B);
   if (it != net->fused.end()) st = it->second;
+  if (st && st->keep_all != net->fused_keep) {   // debug-tap mode changed: rebuild this batch size's state
+    fused_free(st);
+    net->fused.erase(it);
+    st = nullptr;
+  }
   if (!st) {
     // bounded cache of per-batch-size states (planner warm-up at B=2, sampling at B=K, batched sampling at B=R*K)
     if (net->fused.size() >= 4) {
@@ -968,7 +1025,7 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
       fused_free(victim->second);
       net->fused.erase(victim);
     }
-    int rc = build_fused(net, B, 0, stream, &st);
+    int rc = build_fused(net, B, 0, net->fused_keep, stream, &st);
     if (rc != MMDK_OK) return rc;
     net->fused[B] = st;
   }
@@ -1011,6 +1068,7 @@ int unet_fused_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_o
   if (op_index < -1 || op_index + 1 >= (int)st->images.size() || !st->images[op_index + 1].dev)
     return fail(MMDK_EINVAL, "op index out of range (or op has no activation image)");
   if (st->by_slot) return fail(MMDK_EINVAL, "activation taps need the per-tile image mode");
+  if (!st->keep_all) return fail(MMDK_EINVAL, "activation taps need mmdk_unet_debug_keep_activations(net, 1) before the forward");
   const TcImage& im = st->images[op_index + 1];
   if (c_out) *c_out = im.C;
   if (l_out) *l_out = im.L;

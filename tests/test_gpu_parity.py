@@ -65,9 +65,13 @@ def test_unet_tensor_core_matches_oracle(pair, dev, B):
     for t in (3, 24):
         taps = {}
         ref = port.unet_forward(o["P"], x, torch.full((B,), t, dtype=torch.long), taps=taps)
+        # production mode hands activations over inside shared memory; the tap mode also stores them: same eps, bit for bit
+        fast = p["unet"].forward_t(x.to(dev), t, precision="f16x3").clone()
+        h = p["unet"].native()
+        _lib.check(_lib.lib().mmdk_unet_debug_keep_activations(h, 1))
         out = p["unet"].forward_t(x.to(dev), t, precision="f16x3")
         torch.cuda.synchronize()
-        h = p["unet"].native()
+        assert torch.equal(fast, out)
         worst = 0.0
         for j, (name, act) in enumerate(taps["ops"]):
             c, l = C.c_int(), C.c_int()
@@ -78,6 +82,7 @@ def test_unet_tensor_core_matches_oracle(pair, dev, B):
             e = rel_err(buf, act)
             worst = max(worst, e)
             assert e < 5e-5, f"op {j} ({name}) rel_err {e:.3e}"
+        _lib.check(_lib.lib().mmdk_unet_debug_keep_activations(h, 0))
         e = rel_err(out, ref)
         print(f"unet f16x3 B={B} t={t}: eps rel_err={e:.3e}, worst layer {worst:.3e}")
         assert e < 5e-5
