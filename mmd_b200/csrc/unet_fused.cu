@@ -112,7 +112,7 @@ struct FParams {
 
 // barrier slots
 constexpr int B_IN_FULL = 0, B_IN_EMPTY = 2, B_ACC_FULL = 4, B_ACC_EMPTY = 6, B_OUT_DONE = 8, B_W_FULL = 10,
-              B_W_EMPTY = 10 + F_STAGES, B_COUNT = 10 + 2 * F_STAGES;
+              B_W_EMPTY = 10 + F_STAGES, B_PRM_FULL = 10 + 2 * F_STAGES, B_COUNT = 12 + 2 * F_STAGES;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -244,15 +244,24 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
       }
     }
   }
-  // ---- accumulators -> registers, TMEM released ---------------------------------------------------------------------
+  // ---- accumulators -> registers in NLD load steps; step s + 1 is in flight while the statistics of step s are computed ------
   float2 v[NMT][NH / 2];
+  constexpr int NLD = (NMT == 1) ? 2 : NMT;   // one m-tile per step, or the two groups (column halves) of the single m-tile
+  auto tmem_issue = [&](int sidx) {
+    if constexpr (NMT == 1) tmem_ldn<NH / 2>(lane_base + c0 + sidx * (NH / 2), reinterpret_cast<float*>(&v[0][sidx * (NH / 4)]));
+    else tmem_ldn<NH>(lane_base + sidx * N + c0, reinterpret_cast<float*>(v[sidx]));
+  };
+#ifdef F_PIPE_LD
+  tmem_issue(0);
+#else
 #pragma unroll
-  for (int i = 0; i < NMT; ++i) tmem_ldn<NH>(lane_base + i * N + c0, reinterpret_cast<float*>(v[i]));
+  for (int sidx = 0; sidx < NLD; ++sidx) tmem_issue(sidx);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(bar_acc_empty);
   if (c.dbg) c.dbg[8] = clock64();
+#endif
 
   // rows of this thread (one per m-tile) and the first residual panel: its L2-latency load overlaps the statistics
   const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
@@ -282,27 +291,43 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
       b2[2 * k] = make_float2(bq.x, bq.y);
       b2[2 * k + 1] = make_float2(bq.z, bq.w);
     }
+    auto group_stats = [&](int i, int g) {
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < NMT; ++i) {
+      for (int k = 0; k < CPG / 2; ++k) {
+        const float2 t = f2add(v[i][g * (CPG / 2) + k], b2[g * (CPG / 2) + k]);
+        v[i][g * (CPG / 2) + k] = t;
+        s2 = f2add(s2, t);
+      }
+      const float sm = s2.x + s2.y;
+      const float nm = sm * (-1.f / CPG);
+      const float2 nm2 = make_float2(nm, nm);
+      float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float2 s2 = make_float2(0.f, 0.f);
+      for (int k = 0; k < CPG / 2; ++k) {
+        const float2 d = f2add(v[i][g * (CPG / 2) + k], nm2);
+        q2 = f2fma(d, d, q2);
+      }
+      c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, q2.x + q2.y);
+    };
 #pragma unroll
-        for (int k = 0; k < CPG / 2; ++k) {
-          const float2 t = f2add(v[i][g * (CPG / 2) + k], b2[g * (CPG / 2) + k]);
-          v[i][g * (CPG / 2) + k] = t;
-          s2 = f2add(s2, t);
-        }
-        const float sm = s2.x + s2.y;
-        const float nm = sm * (-1.f / CPG);
-        const float2 nm2 = make_float2(nm, nm);
-        float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < CPG / 2; ++k) {
-          const float2 d = f2add(v[i][g * (CPG / 2) + k], nm2);
-          q2 = f2fma(d, d, q2);
-        }
-        c.part[(c.cb * 2 + g) * F_PART_ROWS + 128 * i + c.row] = make_float2(sm, q2.x + q2.y);
+    for (int sidx = 0; sidx < NLD; ++sidx) {
+#ifdef F_PIPE_LD
+      tmem_wait_ld();
+      if (sidx + 1 < NLD) {
+        tmem_issue(sidx + 1);
+      } else {   // everything is in registers: hand the accumulator columns back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(bar_acc_empty);
+        if (c.dbg) c.dbg[8] = clock64();
+      }
+#endif
+      if constexpr (NMT == 1) {
+        group_stats(0, sidx);
+      } else {
+        group_stats(sidx, 0);
+        group_stats(sidx, 1);
       }
     }
   }
@@ -485,6 +510,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       mbar_init(FBAR(B_ACC_FULL + i), 1);
       mbar_init(FBAR(B_ACC_EMPTY + i), FE_WARPS);
       mbar_init(FBAR(B_OUT_DONE + i), FE_WARPS);
+      mbar_init(FBAR(B_PRM_FULL + i), 1);
     }
     for (int s = 0; s < F_STAGES; ++s) { mbar_init(FBAR(B_W_FULL + s), 1); mbar_init(FBAR(B_W_EMPTY + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -510,39 +536,63 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
         if (2 * r_ + par < n_my)
 
   if (warp == F_WARP_IN) {
-    // ================= input producer =================
-    if (lane == 0) {
+    // ================= input producer (lane 0) + per-channel parameter staging (all lanes) =================
+    {
       int uses0 = 0, uses1 = 0, cpar0 = 0, cpar1 = 0, k = 0;
       F_FOR_ITEMS {
         const FOp* op = &P.ops[j];
         const int tile = (int)blockIdx.x + (2 * r_ + par) * G;
         const int slot = P.by_slot ? (int)blockIdx.x * 2 + par : tile;
         const int p = k & 1;
-        // the previous item of this tile parity must have stored its output (also keeps the barrier phases in step)
-        const int cpar = par ? cpar1 : cpar0;
-        if (cpar > 0) mbar_wait(FBAR(B_OUT_DONE + par), (uint32_t)((cpar - 1) & 1));
-        const int big = op->big;
-        if ((big || p == 0) && uses0 > 0) mbar_wait(FBAR(B_IN_EMPTY + 0), (uint32_t)((uses0 - 1) & 1));
-        if ((big || p == 1) && uses1 > 0) mbar_wait(FBAR(B_IN_EMPTY + 1), (uint32_t)((uses1 - 1) & 1));
-        FSTAMP(k, 0);
-        const uint32_t base = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
-        uint32_t total = 0;
-        const int ns = op->in_smem ? 0 : op->n_src;
-        for (int s = 0; s < ns; ++s) total += op->src_tile_bytes[s];
-        if (op->in_smem) mbar_arrive(FBAR(B_IN_FULL + p));   // the previous op's epilogue left the image in the buffer
-        else mbar_expect_tx(FBAR(B_IN_FULL + p), total);
-        for (int s = 0; s < ns; ++s) {
-          const uint32_t tb = op->src_tile_bytes[s];
-          const uint8_t* g = op->src[s] + (size_t)(op->src_by_tile[s] ? tile : slot) * tb;
-          uint32_t off = 0;
-          while (off < tb) {
-            const uint32_t n = min(tb - off, 32768u);
-            bulk_g2s(base + op->src_smem_off[s] + off, g + off, n, FBAR(B_IN_FULL + p));
-            off += n;
+        if (lane == 0) {
+          // the previous item of this tile parity must have stored its output (also keeps the barrier phases in step)
+          const int cpar = par ? cpar1 : cpar0;
+          if (cpar > 0) mbar_wait(FBAR(B_OUT_DONE + par), (uint32_t)((cpar - 1) & 1));
+          const int big = op->big;
+          if ((big || p == 0) && uses0 > 0) mbar_wait(FBAR(B_IN_EMPTY + 0), (uint32_t)((uses0 - 1) & 1));
+          if ((big || p == 1) && uses1 > 0) mbar_wait(FBAR(B_IN_EMPTY + 1), (uint32_t)((uses1 - 1) & 1));
+          FSTAMP(k, 0);
+          const uint32_t base = smem_base + (big ? 0u : (uint32_t)p * P.buf_bytes);
+          uint32_t total = 0;
+          const int ns = op->in_smem ? 0 : op->n_src;
+          for (int s = 0; s < ns; ++s) total += op->src_tile_bytes[s];
+          if (op->in_smem) mbar_arrive(FBAR(B_IN_FULL + p));   // the previous op's epilogue left the image in the buffer
+          else mbar_expect_tx(FBAR(B_IN_FULL + p), total);
+          for (int s = 0; s < ns; ++s) {
+            const uint32_t tb = op->src_tile_bytes[s];
+            const uint8_t* g = op->src[s] + (size_t)(op->src_by_tile[s] ? tile : slot) * tb;
+            uint32_t off = 0;
+            while (off < tb) {
+              const uint32_t n = min(tb - off, 32768u);
+              bulk_g2s(base + op->src_smem_off[s] + off, g + off, n, FBAR(B_IN_FULL + p));
+              off += n;
+            }
           }
         }
-        if (big || p == 0) uses0++;
-        if (big || p == 1) uses1++;
+        __syncwarp();
+        // Parameters of this item -> bank k & 1.  The bank was last read by item k - 2, whose epilogue has finished: lane 0
+        // waited for the OUT_DONE of an item >= k - 2 above, and epilogues complete in item order.
+        {
+          float* bank = reinterpret_cast<float*>(smem + P.off_prm + (uint32_t)p * (F_MAX_N * 20));
+          const float* cond = (op->cond_off >= 0) ? P.cond_row + op->cond_off : nullptr;
+          const int Nn = op->N;
+          for (int ch = lane; ch < Nn; ch += 32) {
+            const float vb = (ch < op->cout) ? __ldg(op->bias + ch) : 0.f;
+            const float vg = op->gamma ? __ldg(op->gamma + ch) : 1.f;
+            const float ve = op->beta ? __ldg(op->beta + ch) : 0.f;
+            const float vc = cond ? __ldg(cond + ch) : 0.f;
+            const float vr = op->res_bias ? __ldg(op->res_bias + ch) : 0.f;
+            bank[ch] = vb;
+            bank[F_MAX_N + ch] = vg;
+            bank[2 * F_MAX_N + ch] = ve;
+            bank[3 * F_MAX_N + ch] = vc;
+            bank[4 * F_MAX_N + ch] = vr;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(FBAR(B_PRM_FULL + p));
+        }
+        if (op->big || p == 0) uses0++;
+        if (op->big || p == 1) uses1++;
         if (par) cpar1++; else cpar0++;
         k++;
       }
@@ -677,17 +727,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       c.sbuf = smem + (size_t)((2 * r_ + 1 < n_my) ? p : (p ^ 1)) * P.buf_bytes;
       c.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg + (size_t)k * 16 : nullptr;
       if (tid == 0) FSTAMP(k, 7);
-      // per-channel parameters of this op while its MMAs run
-      const int N = op->N;
-      if (tid < N) {
-        const float* cond = (op->cond_off >= 0) ? P.cond_row + op->cond_off : nullptr;
-        c.p_bias[tid] = (tid < op->cout) ? __ldg(op->bias + tid) : 0.f;
-        c.p_gamma[tid] = op->gamma ? __ldg(op->gamma + tid) : 1.f;
-        c.p_beta[tid] = op->beta ? __ldg(op->beta + tid) : 0.f;
-        c.p_cond[tid] = cond ? __ldg(cond + tid) : 0.f;
-        c.p_rb[tid] = op->res_bias ? __ldg(op->res_bias + tid) : 0.f;
-      }
-      epi_bar16();
+      // per-channel parameters of this item: staged by the producer warp into bank p
+      mbar_wait(FBAR(B_PRM_FULL + p), (uint32_t)((p ? nuse1 : nuse0) & 1));
       mbar_wait(FBAR(B_ACC_FULL + p), (uint32_t)((p ? nuse1 : nuse0) & 1));
       tc_fence_after();
       if (tid == 0) FSTAMP(k, 3);
