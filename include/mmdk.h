@@ -37,6 +37,7 @@ extern "C" {
 #define MMDK_MAX_HARD_ROWS 4
 #define MMDK_STATE_DIM 4
 #define MMDK_PEER_GRID_MAX 32
+#define MMDK_MAX_RANKS 8
 
 /* Thread-local message of the last failing call. */
 const char* mmdk_last_error(void);
@@ -167,6 +168,9 @@ typedef struct {
   const float* peer_sorted_dev;
   int peer_grid;
   float peer_grid_lo, peer_grid_inv_cell;
+  /* Double-buffered peer table (mmdk_peer_exchange): when not NULL, peers_dev is [2][n_peers, H, 2] and readers use half
+   * (*peer_seq_dev & 1); NULL = peers_dev is a single [n_peers, H, 2] table. */
+  const uint32_t* peer_seq_dev;
 } mmdk_groups;
 
 /* One evaluation of GuideManagerTrajectoriesWithVelocity.forward (guides.py:180-226): grad_dev [B,H,D] =
@@ -196,6 +200,41 @@ typedef struct {
 int mmdk_ddpm_step(const mmdk_guide_env* env, const mmdk_groups* groups, const mmdk_step_scalars* sc, int H,
                    float* x_dev, const float* eps_dev, const float* noise_dev, float* chain_dev, void* stream);
 
+/* Lock-step exchange over peer memory -- the all-gather of the representative paths fused into the step kernel:
+ * at the END of a reverse step every group's representative sample (the x the next step starts from, unnormalised like
+ * mmdk_publish_peers) is stored straight into the peer table of EVERY rank of the fleet (NVLink / NVSwitch stores through
+ * CUDA-IPC mappings), and the last group of a rank releases the rank's sequence number into every rank's flag array;
+ * mmdk_wait_peers is the matching acquire.  Tables are double buffered by sequence parity: [2][n_rows][H][2] fp32.
+ *   tables_dev[r], flags_dev[r]: rank r's table / flag array ([MMDK_MAX_RANKS] uint32) as mapped on THIS device (own
+ *   allocation for r == rank, mmdk_p2p_open of rank r's exported handle otherwise; flags unused when world == 1).
+ *   state_dev: local uint32[4] = {publish sequence, consume sequence, group counter, error flag (a peer never arrived)}.
+ * Readers (step kernel brute-force path, mmdk_build_peer_hash) select the half with mmdk_groups.peer_seq_dev =
+ * state_dev + 1 (world > 1: advanced by mmdk_wait_peers) or state_dev + 0 (world == 1: stream order is enough). */
+typedef struct {
+  int world, rank;
+  int row_offset;   /* table row of this call's first group */
+  int n_rows;       /* rows of one table half = robots of the whole fleet */
+  int rep_index;    /* representative sample of every group */
+  float* tables_dev[MMDK_MAX_RANKS];
+  uint32_t* flags_dev[MMDK_MAX_RANKS];
+  uint32_t* state_dev;
+} mmdk_peer_exchange;
+
+/* mmdk_ddpm_step followed by the publication (exchange == NULL: plain mmdk_ddpm_step).  With scalars that leave x unchanged
+ * (do_posterior = n_guide_steps = add_noise = final_hard_conds = 0) it is a pure publication of the current x. */
+int mmdk_ddpm_step_publish(const mmdk_guide_env* env, const mmdk_groups* groups, const mmdk_step_scalars* sc, int H,
+                           float* x_dev, const float* eps_dev, const float* noise_dev, float* chain_dev,
+                           const mmdk_peer_exchange* exchange, void* stream);
+/* Blocks the STREAM (not the host) until every rank has published its next sequence number to this rank (world > 1). */
+int mmdk_wait_peers(const mmdk_peer_exchange* exchange, void* stream);
+
+/* Peer-memory plumbing: zero-initialised cudaMalloc allocations and their CUDA-IPC handles (64 bytes). */
+int mmdk_p2p_alloc(size_t bytes, void** out_dev);
+int mmdk_p2p_free(void* dev);
+int mmdk_p2p_export(void* dev, unsigned char handle[64]);
+int mmdk_p2p_open(const unsigned char handle[64], void** out_dev);
+int mmdk_p2p_close(void* dev);
+
 /* The whole reverse loop of p_sample_loop (diffusion_model_base.py:163-211) in ONE call: for every step i
  *   [lockstep, guided steps only: mmdk_publish_peers -> mmdk_build_peer_hash]  ->  mmdk_unet_forward(t_index[i])  ->
  *   mmdk_ddpm_step(scalars[i], noise frame i, chain frame i)
@@ -211,6 +250,9 @@ typedef struct {
   int lockstep;
   int rep_index;
   float* peers_local_dev;
+  /* not NULL: lock-step publication fused into the step kernels (mmdk_ddpm_step_publish / mmdk_wait_peers) -- also across
+   * processes, so a sharded fleet's chain is one captured graph too; peers_local_dev is ignored */
+  const mmdk_peer_exchange* exchange;
 } mmdk_chain_desc;
 
 int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* env, const mmdk_groups* groups,
@@ -224,9 +266,10 @@ int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, in
 
 /* Builds the spatial hash of a lock-step peer table peers_dev [n_peers, H, 2] (see mmdk_groups): replaces the
  * reference's dense (n_constraints, B, H, 2) distance tensor (cost_functions.py:304-324) by an O(neighbours) lookup.
- * grid <= MMDK_PEER_GRID_MAX; the caller chooses grid / lo / inv_cell with 1 / inv_cell >= peer_radius. */
-int mmdk_build_peer_hash(const float* peers_dev, int n_peers, int H, int grid, float grid_lo, float grid_inv_cell,
-                         uint16_t* cell_start_dev, float* sorted_dev, void* stream);
+ * grid <= MMDK_PEER_GRID_MAX; the caller chooses grid / lo / inv_cell with 1 / inv_cell >= peer_radius.  seq_dev != NULL:
+ * peers_dev is the double-buffered table of a mmdk_peer_exchange and half (*seq_dev & 1) is hashed. */
+int mmdk_build_peer_hash(const float* peers_dev, const uint32_t* seq_dev, int n_peers, int H, int grid, float grid_lo,
+                         float grid_inv_cell, uint16_t* cell_start_dev, float* sorted_dev, void* stream);
 
 /* apply_cross_conditioning (sample_functions.py:17-31) for one (m1, ind1) <- (m2, ind2) stitch of an ensemble:
  * x1[:, ind1, :] = min(x2[:, ind2, :] + rel, bnd); x2[:, ind2, :] = max(x1[:, ind1, :] - rel, -bnd). */

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmdk.so")
 
 MMDK_OK, MMDK_EINVAL, MMDK_ECUDA, MMDK_ENOMEM = 0, 1, 2, 3
-MAX_LEVELS, MAX_HARD_ROWS, STATE_DIM = 4, 4, 4
+MAX_LEVELS, MAX_HARD_ROWS, STATE_DIM, MAX_RANKS = 4, 4, 4, 8
 UNET_FP32, UNET_F16X3, UNET_F16X3_LAYERS = 0, 1, 2
 UNET_MODES = {"fp32": UNET_FP32, "f16x3": UNET_F16X3, "tc": UNET_F16X3, "f16x3_layers": UNET_F16X3_LAYERS}
 
@@ -38,7 +38,7 @@ class Groups(C.Structure):
                 ("cons_dev", C.c_void_p), ("peers_dev", C.c_void_p), ("peer_self_dev", C.c_void_p),
                 ("n_peers", C.c_int), ("peer_radius", C.c_float), ("peer_weight", C.c_float),
                 ("peer_cell_start_dev", C.c_void_p), ("peer_sorted_dev", C.c_void_p), ("peer_grid", C.c_int),
-                ("peer_grid_lo", C.c_float), ("peer_grid_inv_cell", C.c_float)]
+                ("peer_grid_lo", C.c_float), ("peer_grid_inv_cell", C.c_float), ("peer_seq_dev", C.c_void_p)]
 
 
 class StepScalars(C.Structure):
@@ -49,15 +49,22 @@ class StepScalars(C.Structure):
                 ("final_hard_conds", C.c_int)]
 
 
+class PeerExchange(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("row_offset", C.c_int), ("n_rows", C.c_int), ("rep_index", C.c_int),
+                ("tables_dev", C.c_void_p * MAX_RANKS), ("flags_dev", C.c_void_p * MAX_RANKS), ("state_dev", C.c_void_p)]
+
+
 class ChainDesc(C.Structure):
     _fields_ = [("n_steps", C.c_int), ("t_index", C.POINTER(C.c_int)), ("scalars", C.POINTER(StepScalars)),
-                ("lockstep", C.c_int), ("rep_index", C.c_int), ("peers_local_dev", C.c_void_p)]
+                ("lockstep", C.c_int), ("rep_index", C.c_int), ("peers_local_dev", C.c_void_p),
+                ("exchange", C.POINTER(PeerExchange))]
 
 
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
-    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_unet_debug_stamps", "mmdk_unet_debug_keep_activations", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
+    "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_unet_debug_stamps", "mmdk_unet_debug_keep_activations", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_ddpm_step_publish", "mmdk_wait_peers", "mmdk_p2p_alloc", "mmdk_p2p_free", "mmdk_p2p_export",
+    "mmdk_p2p_open", "mmdk_p2p_close", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize", "mmdk_get_conflicts", "mmdk_smooth_trajs",
 ]
 
@@ -95,7 +102,15 @@ def load():
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
     lib.mmdk_run_chain.argtypes = [vp, i, C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(ChainDesc), i, vp, vp, vp, vp, i, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]
-    lib.mmdk_build_peer_hash.argtypes = [vp, i, i, i, f, f, vp, vp, vp]
+    lib.mmdk_build_peer_hash.argtypes = [vp, vp, i, i, i, f, f, vp, vp, vp]
+    lib.mmdk_ddpm_step_publish.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp,
+                                           C.POINTER(PeerExchange), vp]
+    lib.mmdk_wait_peers.argtypes = [C.POINTER(PeerExchange), vp]
+    lib.mmdk_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.mmdk_p2p_free.argtypes = [vp]
+    lib.mmdk_p2p_export.argtypes = [vp, C.c_char_p]
+    lib.mmdk_p2p_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.mmdk_p2p_close.argtypes = [vp]
     lib.mmdk_cross_condition.argtypes = [vp, vp, i, i, i, i, C.c_float * 4, C.c_float * 4, vp]
     lib.mmdk_q_sample.argtypes = [vp, vp, f, f, i64, vp, vp]
     lib.mmdk_cell_index.argtypes = [C.POINTER(GuideEnv), vp, i64, vp, vp]

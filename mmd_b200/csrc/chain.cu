@@ -53,23 +53,41 @@ static int issue_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env
                        cudaStream_t s) {
   const size_t B = (size_t)groups->n_groups * groups->K;
   const size_t frame = B * H * MMDK_STATE_DIM;
+  const mmdk_peer_exchange* ex = ch->exchange;
+  auto lock_guided = [&](int i) {
+    return i >= 0 && i < ch->n_steps && ch->lockstep && ch->scalars[i].n_guide_steps > 0 && groups->n_peers > 1 && groups->peers_dev;
+  };
+  bool published = false;   // the previous step kernel already published the current x
   for (int i = 0; i < ch->n_steps; ++i) {
     const mmdk_step_scalars& sc = ch->scalars[i];
-    if (ch->lockstep && sc.n_guide_steps > 0 && groups->n_peers > 1 && groups->peers_dev) {
-      // every group publishes its representative sample into its row of the peer table (single rank: the table IS local)
-      int rc = mmdk_publish_peers(env, groups->n_groups, groups->K, H, ch->rep_index, x, ch->peers_local_dev, s);
-      if (rc != MMDK_OK) return rc;
+    if (lock_guided(i)) {
+      int rc;
+      if (ex) {
+        if (!published) {   // first guided step of the chain: a pure publication of the current x (x <- x)
+          mmdk_step_scalars idle = sc;
+          idle.do_posterior = 0; idle.n_guide_steps = 0; idle.add_noise = 0; idle.final_hard_conds = 0;
+          rc = mmdk_ddpm_step_publish(env, groups, &idle, H, x, nullptr, nullptr, nullptr, ex, s);
+          if (rc != MMDK_OK) return rc;
+        }
+        rc = mmdk_wait_peers(ex, s);
+        if (rc != MMDK_OK) return rc;
+      } else {
+        // every group publishes its representative sample into its row of the peer table (single rank: the table IS local)
+        rc = mmdk_publish_peers(env, groups->n_groups, groups->K, H, ch->rep_index, x, ch->peers_local_dev, s);
+        if (rc != MMDK_OK) return rc;
+      }
       if (groups->peer_cell_start_dev) {
-        rc = mmdk_build_peer_hash(groups->peers_dev, groups->n_peers, H, groups->peer_grid, groups->peer_grid_lo,
-                                  groups->peer_grid_inv_cell, const_cast<uint16_t*>(groups->peer_cell_start_dev),
-                                  const_cast<float*>(groups->peer_sorted_dev), s);
+        rc = mmdk_build_peer_hash(groups->peers_dev, groups->peer_seq_dev, groups->n_peers, H, groups->peer_grid,
+                                  groups->peer_grid_lo, groups->peer_grid_inv_cell,
+                                  const_cast<uint16_t*>(groups->peer_cell_start_dev), const_cast<float*>(groups->peer_sorted_dev), s);
         if (rc != MMDK_OK) return rc;
       }
     }
     int rc = mmdk_unet_forward(net, unet_mode, x, (int)B, ch->t_index[i], eps, s);
     if (rc != MMDK_OK) return rc;
-    rc = mmdk_ddpm_step(env, groups, &sc, H, x, eps, noise ? noise + (size_t)i * frame : nullptr,
-                        chain_out ? chain_out + (size_t)i * frame : nullptr, s);
+    published = ex && lock_guided(i + 1);   // this step's kernel publishes the x the next (guided) step starts from
+    rc = mmdk_ddpm_step_publish(env, groups, &sc, H, x, eps, noise ? noise + (size_t)i * frame : nullptr,
+                                chain_out ? chain_out + (size_t)i * frame : nullptr, published ? ex : nullptr, s);
     if (rc != MMDK_OK) return rc;
   }
   return MMDK_OK;
@@ -86,7 +104,10 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
                    float* chain_out_dev, int use_graph, void* stream) {
   if (!net || !env || !groups || !chain || !x_dev || !eps_dev) return fail(MMDK_EINVAL, "null argument");
   if (chain->n_steps < 1 || !chain->scalars || !chain->t_index) return fail(MMDK_EINVAL, "empty chain description");
-  if (chain->lockstep && groups->peers_dev && !chain->peers_local_dev) return fail(MMDK_EINVAL, "lockstep needs peers_local_dev");
+  if (chain->lockstep && groups->peers_dev && !chain->peers_local_dev && !chain->exchange)
+    return fail(MMDK_EINVAL, "lockstep needs peers_local_dev or an exchange");
+  if (chain->exchange && groups->peers_dev && !groups->peer_seq_dev)
+    return fail(MMDK_EINVAL, "an exchange publishes into a double-buffered table: set groups->peer_seq_dev");
   cudaStream_t s = (cudaStream_t)stream;
   if (!use_graph) return issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, s);
 
@@ -108,6 +129,8 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
   key.words.push_back((uint64_t)(uintptr_t)noise_dev);
   key.words.push_back((uint64_t)(uintptr_t)chain_out_dev);
   key.words.push_back((uint64_t)(uintptr_t)chain->peers_local_dev);
+  if (chain->exchange) push_bytes(key, chain->exchange, sizeof(*chain->exchange));
+  else key.words.push_back(0);
   push_bytes(key, env, sizeof(*env));
   push_bytes(key, groups, sizeof(*groups));
   push_bytes(key, chain->scalars, sizeof(mmdk_step_scalars) * chain->n_steps);

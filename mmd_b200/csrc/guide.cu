@@ -15,11 +15,63 @@
 // discontinuities downstream (floor to a grid cell, hinge, in/out of radius) make single-rounding FMAs visible.
 #include <cooperative_groups.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace mmdk {
+
+constexpr int kMaxIters = 32;   // guide iterations per launch served by the lazy cluster flag exchange
+
+struct PubArgs {
+  int world, rank, row_offset, n_rows;   // ranks of the fleet, this rank, first table row of this launch's groups, rows per table
+  float* tables[MMDK_MAX_RANKS];         // peer table of every rank as mapped on THIS device: [2][n_rows][H][2] (world == 1: [n_rows][H][2])
+  uint32_t* flags[MMDK_MAX_RANKS];       // flag array of every rank: flags[r][q] = last sequence number rank q published to rank r
+  uint32_t* state;                       // local: [0] publish sequence, [1] consume sequence, [2] group counter, [3] error flag
+};
+
+__device__ __forceinline__ void st_release_cluster(int* p, int v) {
+  asm volatile("st.release.cluster.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cluster(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cluster.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The normaliser's clip decision of a group (any element outside [-1 - 1e-4, 1 + 1e-4] => clamp everything to [-1, 1]) only
+// changes a thread's result if one of ITS elements lies outside [-1, 1].  So the CTAs of a group never barrier on it: each
+// CTA stores its flag into slot [round][rank] of every CTA of the cluster (release) and only the (rare) threads that hold an
+// element in the ambiguous band, with no flagged element in their own CTA, wait for the other CTAs' slots (acquire).
+struct GroupFlag {
+  int* slots;   // [kMaxIters + 1][16] in this CTA's shared memory, -1 = not yet published
+  int cpg, rank, tid;
+
+  __device__ __forceinline__ int decide(int round, int mine, int band) const {
+    const int cta_flag = __syncthreads_or(mine);
+    if (cpg == 1) return cta_flag;
+    if (tid < cpg) st_release_cluster(cg::this_cluster().map_shared_rank(slots + round * 16 + rank, tid), cta_flag);
+    int flag = cta_flag;
+    if (!flag && band) {
+      for (int r = 0; r < cpg; ++r) {
+        int f;
+        while ((f = ld_acquire_cluster(slots + round * 16 + r)) < 0) {}
+        flag |= f;
+      }
+    }
+    return flag;
+  }
+};
 
 struct StepArgs {
   mmdk_guide_env env;
@@ -37,6 +89,12 @@ struct StepArgs {
   int n_costs_max;
   int peers_in_smem;  // the [n_peers, H, 2] table is staged in shared memory once per launch (it is constant during it)
   int hash_in_smem;   // the peer hash (cell_start + sorted) is staged in shared memory once per launch
+  // publication of every group's representative sample at the END of the step (it is the x the next step starts from):
+  // fused all-gather over peer memory -- the row goes straight into the peer table of every rank (NVLink stores), then
+  // the last group to finish releases this rank's sequence number into every rank's flag array
+  int pub_on;
+  int pub_rep;        // representative sample of a group
+  PubArgs pub;
 };
 
 __device__ __forceinline__ void clip_by_norm(float g[4], float max_norm) {
@@ -74,7 +132,7 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
   // exactly two waves of 16 clusters x 16 CTAs (round 2: 1024-thread CTAs in clusters of 8 kept only 15 clusters = 120 SMs
   // resident and needed three waves for 2.13 waves of work)
   extern __shared__ float4 s_xu_all[];   // [2][spc][H] unnormalised states of this CTA's samples, double buffered
-  __shared__ int s_flags[2][16];     // per-iteration clip flags of the cluster's CTAs (double buffered)
+  __shared__ int s_flags[(kMaxIters + 1) * 16];   // clip flags of the cluster's CTAs, one row per guide iteration + publication
 
   const int H = a.H;
   const int tid = threadIdx.x;
@@ -88,7 +146,8 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
   const size_t off = (b * H + h) * 4;
   const mmdk_guide_env& E = a.env;
 
-  if (tid < 32) { s_flags[0][tid & 15] = 0; s_flags[1][tid & 15] = 0; }
+  for (int i = tid; i < (kMaxIters + 1) * 16; i += blockDim.x) s_flags[i] = -1;
+  const GroupFlag gflag{s_flags, a.cpg, rank, tid};
 
   // hard conditions of this group that hit my waypoint (last one wins, dict order)
   bool hc = false;
@@ -129,8 +188,11 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
   float2* s_peers = reinterpret_cast<float2*>(s_xu_all + 2 * (size_t)a.spc * H);
   float4* s_sorted = reinterpret_cast<float4*>(s_peers);                                  // hash staging aliases the
   unsigned short* s_cs = reinterpret_cast<unsigned short*>(s_sorted + (size_t)H * a.grp.n_peers);   // brute-force staging
+  // double-buffered table: readers use the half of the current sequence number, the publication at the end of this launch
+  // writes the other half
+  const size_t peer_half = (a.grp.peers_dev && a.grp.peer_seq_dev) ? (size_t)(*a.grp.peer_seq_dev & 1u) * a.grp.n_peers * H : 0;
   if (a.grp.peers_dev && a.peers_in_smem && !a.grp.peer_cell_start_dev) {
-    const float2* gp = reinterpret_cast<const float2*>(a.grp.peers_dev);
+    const float2* gp = reinterpret_cast<const float2*>(a.grp.peers_dev) + peer_half;
     for (int i = tid; i < a.grp.n_peers * H; i += blockDim.x) s_peers[i] = __ldg(gp + i);
     __syncthreads();
   }
@@ -148,22 +210,15 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
 
   for (int it = 0; it < n_iter; ++it) {
     // ---- G3: LimitsNormalizer.unnormalize with its global, data-dependent clip ------------------------------
-    int local = 0;
+    int mine = 0, band = 0;
     if (valid) {
 #pragma unroll
-      for (int d = 0; d < 4; ++d) local |= (x[d] > 1.0001f) | (x[d] < -1.0001f);
-    }
-    int flag = __syncthreads_or(local);
-    if (a.cpg > 1) {
-      cg::cluster_group cl = cg::this_cluster();
-      if (tid < a.cpg) {
-        int* remote = cl.map_shared_rank(&s_flags[it & 1][rank], tid);
-        *remote = flag;
+      for (int d = 0; d < 4; ++d) {
+        mine |= (x[d] > 1.0001f) | (x[d] < -1.0001f);
+        band |= (x[d] > 1.f) | (x[d] < -1.f);
       }
-      cl.sync();
-      flag = 0;
-      for (int r = 0; r < a.cpg; ++r) flag |= s_flags[it & 1][r];
     }
+    const int flag = gflag.decide(it, mine, band);
     float xu[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
@@ -294,7 +349,7 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
           }
         }
       } else {
-        const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev)) + h;
+        const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev) + peer_half) + h;
 #pragma unroll 4
         for (int j = 0; j < a.grp.n_peers; ++j, pq += H) {
           if (j == self_peer) continue;
@@ -337,6 +392,48 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
       float4 v = make_float4(x[0], x[1], x[2], x[3]);
       *reinterpret_cast<float4*>(a.x + off) = v;
       if (a.chain) *reinterpret_cast<float4*>(a.chain + off) = v;
+    }
+    if (a.pub_on) {
+      // ---- lock-step publication (mmdk_publish_peers semantics) of the x the NEXT step starts from ---------------------
+      int mine = 0, band = 0;
+      if (valid) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          mine |= (x[d] > 1.0001f) | (x[d] < -1.0001f);
+          band |= (x[d] > 1.f) | (x[d] < -1.f);
+        }
+      }
+      const bool is_rep = valid && (sidx == a.pub_rep);
+      const int flag = gflag.decide(kMaxIters, mine, is_rep ? band : 0);
+      const PubArgs& pb = a.pub;
+      if (is_rep) {
+        float q[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          float v = flag ? fminf(fmaxf(x[d], -1.f), 1.f) : x[d];
+          v = (v + 1.f) / 2.f;
+          q[d] = v * E.norm_range[d] + E.norm_min[d];
+        }
+        // table half of the sequence number this publication will get (read before anybody can advance it: the advance
+        // happens after every group of this launch has arrived at the counter below)
+        const uint32_t half = (pb.world > 1) ? ((pb.state[0] + 1u) & 1u) : 0u;
+        const size_t row = ((size_t)half * pb.n_rows + pb.row_offset + g) * H + h;
+        for (int r = 0; r < pb.world; ++r) reinterpret_cast<float2*>(pb.tables[r])[row] = make_float2(q[0], q[1]);
+        if (pb.world > 1) __threadfence_system();
+      }
+      if (pb.world > 1) {
+        __syncthreads();   // the representative's H threads have fenced their remote stores
+        if (is_rep && h == 0) {
+          const uint32_t prev = atomicAdd(pb.state + 2, 1u);
+          if (prev == (uint32_t)a.grp.n_groups - 1u) {   // last group of this rank: release the sequence number everywhere
+            pb.state[2] = 0u;
+            const uint32_t seq = pb.state[0] + 1u;
+            pb.state[0] = seq;
+            __threadfence_system();
+            for (int r = 0; r < pb.world; ++r) st_release_sys(pb.flags[r] + pb.rank, seq);
+          }
+        }
+      }
     }
   }
   if (a.cpg > 1) cg::this_cluster().sync();  // nobody exits while a peer may still write its flags
@@ -398,6 +495,7 @@ static int plan_step(StepArgs& a) {
   if (H < 2 || H > 256 || (H & 1)) return fail(MMDK_EINVAL, "horizon must be even and in [2, 256]");
   if (H > 512) return fail(MMDK_EINVAL, "horizon too long");
   if (K < 1 || a.grp.n_groups < 1) return fail(MMDK_EINVAL, "n_groups and K must be >= 1");
+  if (a.sc.n_guide_steps > kMaxIters) return fail(MMDK_EINVAL, "n_guide_steps > 32 is not supported by the step kernel");
   if (!a.grp.hard_rows_dev || !a.grp.hard_vals_dev) return fail(MMDK_EINVAL, "hard condition arrays are required");
   int max_spc = 512 / H;
   int spc = K < max_spc ? K : max_spc;
@@ -425,27 +523,48 @@ __global__ void publish_peers_kernel(mmdk_guide_env E, int K, int H, int rep, co
                                      float* __restrict__ out) {
   // one CTA per group: global clip flag over the group's [K,H,D] block, then unnormalise the representative sample
   const int g = blockIdx.x;
-  const float* xg = x + (size_t)g * K * H * 4;
+  const float4* xg = reinterpret_cast<const float4*>(x + (size_t)g * K * H * 4);
   int local = 0;
-  for (int i = threadIdx.x; i < K * H * 4; i += blockDim.x) {
-    float v = xg[i];
-    local |= (v > 1.0001f) | (v < -1.0001f);
+  for (int i = threadIdx.x; i < K * H; i += blockDim.x) {
+    const float4 v = xg[i];
+    local |= (v.x > 1.0001f) | (v.x < -1.0001f) | (v.y > 1.0001f) | (v.y < -1.0001f) | (v.z > 1.0001f) | (v.z < -1.0001f) |
+             (v.w > 1.0001f) | (v.w < -1.0001f);
   }
   int flag = __syncthreads_or(local);
   for (int i = threadIdx.x; i < H * 2; i += blockDim.x) {
     int h = i >> 1, d = i & 1;
-    float v = xg[((size_t)rep * H + h) * 4 + d];
+    float v = x[((size_t)g * K * H + (size_t)rep * H + h) * 4 + d];
     if (flag) v = fminf(fmaxf(v, -1.f), 1.f);
     v = (v + 1.f) / 2.f;
     out[((size_t)g * H + h) * 2 + d] = v * E.norm_range[d] + E.norm_min[d];
   }
 }
 
+// Consumer side of the fused publication: waits until every rank's sequence number in THIS rank's flag array has reached
+// the next expected value, then advances the consume sequence (state[1]).  Bounded spin: a dead peer sets state[3].
+__global__ void wait_peers_kernel(PubArgs pb) {
+  const int r = threadIdx.x;
+  const uint32_t expect = pb.state[1] + 1u;
+  if (r < pb.world) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(ld_acquire_sys(pb.flags[pb.rank] + r) - expect) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) { pb.state[3] = 1u; break; }   // 4 s
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  if (r == 0) pb.state[1] = expect;
+}
+
 // Lock-step peer hash: one CTA per waypoint h.  Stable counting sort of the [n_peers] positions of waypoint h into a
 // G x G uniform grid (cell >= peer radius): cell_start [H][G*G+1] (uint16), sorted [H][n_peers] float4 (x, y, index, 0).
 // Stable (peers of a cell stay in index order), so the query visits candidates in a deterministic order.
-__global__ void build_peer_hash_kernel(const float* __restrict__ peers, int n_peers, int H, int G, float lo, float inv_cell,
-                                       unsigned short* __restrict__ cell_start, float4* __restrict__ sorted) {
+__global__ void build_peer_hash_kernel(const float* __restrict__ peers_base, const uint32_t* __restrict__ seq, int n_peers, int H,
+                                       int G, float lo, float inv_cell, unsigned short* __restrict__ cell_start,
+                                       float4* __restrict__ sorted) {
+  const float* peers = peers_base + (seq ? (size_t)(*seq & 1u) * n_peers * H * 2 : 0);
   extern __shared__ int s_hash[];            // [G*G+1] counts / offsets, then [n_peers] cell of every peer
   int* s_cnt = s_hash;
   int* s_cell = s_hash + G * G + 1;
@@ -618,22 +737,92 @@ int mmdk_ddpm_step(const mmdk_guide_env* env, const mmdk_groups* groups, const m
   return launch_step(a, false, (cudaStream_t)stream);
 }
 
+static int fill_pub(StepArgs& a, const mmdk_peer_exchange* ex) {
+  if (!ex) { a.pub_on = 0; return MMDK_OK; }
+  if (ex->world < 1 || ex->world > MMDK_MAX_RANKS || ex->rank < 0 || ex->rank >= ex->world)
+    return fail(MMDK_EINVAL, "peer exchange: bad world / rank");
+  if (!ex->state_dev) return fail(MMDK_EINVAL, "peer exchange: state_dev is required");
+  if (ex->rep_index < 0 || ex->rep_index >= a.grp.K) return fail(MMDK_EINVAL, "peer exchange: rep_index out of range");
+  if (ex->row_offset < 0 || ex->row_offset + a.grp.n_groups > ex->n_rows) return fail(MMDK_EINVAL, "peer exchange: rows out of range");
+  a.pub_on = 1;
+  a.pub_rep = ex->rep_index;
+  a.pub.world = ex->world; a.pub.rank = ex->rank; a.pub.row_offset = ex->row_offset; a.pub.n_rows = ex->n_rows;
+  a.pub.state = ex->state_dev;
+  for (int r = 0; r < ex->world; ++r) {
+    if (!ex->tables_dev[r] || (ex->world > 1 && !ex->flags_dev[r])) return fail(MMDK_EINVAL, "peer exchange: null table / flag pointer");
+    a.pub.tables[r] = ex->tables_dev[r];
+    a.pub.flags[r] = ex->flags_dev[r];
+  }
+  return MMDK_OK;
+}
+
+int mmdk_ddpm_step_publish(const mmdk_guide_env* env, const mmdk_groups* groups, const mmdk_step_scalars* sc, int H,
+                           float* x_dev, const float* eps_dev, const float* noise_dev, float* chain_dev,
+                           const mmdk_peer_exchange* exchange, void* stream) {
+  if (!env || !groups || !sc || !x_dev) return fail(MMDK_EINVAL, "null argument");
+  if (sc->do_posterior && !eps_dev) return fail(MMDK_EINVAL, "eps_dev required when do_posterior is set");
+  StepArgs a{};
+  a.env = *env; a.grp = *groups; a.sc = *sc; a.H = H;
+  a.x = x_dev; a.eps = eps_dev; a.noise = noise_dev; a.chain = chain_dev;
+  int rc = plan_step(a);
+  if (rc != MMDK_OK) return rc;
+  rc = fill_pub(a, exchange);
+  if (rc != MMDK_OK) return rc;
+  return launch_step(a, false, (cudaStream_t)stream);
+}
+
+int mmdk_wait_peers(const mmdk_peer_exchange* ex, void* stream) {
+  if (!ex || !ex->state_dev) return fail(MMDK_EINVAL, "null argument");
+  if (ex->world <= 1) return MMDK_OK;
+  if (ex->world > MMDK_MAX_RANKS || !ex->flags_dev[ex->rank]) return fail(MMDK_EINVAL, "peer exchange: bad world / flags");
+  PubArgs pb{};
+  pb.world = ex->world; pb.rank = ex->rank; pb.state = ex->state_dev;
+  for (int r = 0; r < ex->world; ++r) pb.flags[r] = ex->flags_dev[r];
+  wait_peers_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pb);
+  return check_cuda(cudaGetLastError(), "wait_peers_kernel");
+}
+
+// ---- peer-memory plumbing for the exchange: plain cudaMalloc allocations shared through CUDA IPC -----------------------------
+int mmdk_p2p_alloc(size_t bytes, void** out_dev) {
+  if (!out_dev || bytes == 0) return fail(MMDK_EINVAL, "null argument");
+  MMDK_CUDA(cudaMalloc(out_dev, bytes));
+  MMDK_CUDA(cudaMemset(*out_dev, 0, bytes));
+  return MMDK_OK;
+}
+int mmdk_p2p_free(void* dev) { return check_cuda(cudaFree(dev), "cudaFree"); }
+int mmdk_p2p_export(void* dev, unsigned char handle[64]) {
+  if (!dev || !handle) return fail(MMDK_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  MMDK_CUDA(cudaIpcGetMemHandle(&h, dev));
+  memcpy(handle, &h, 64);
+  return MMDK_OK;
+}
+int mmdk_p2p_open(const unsigned char handle[64], void** out_dev) {
+  if (!handle || !out_dev) return fail(MMDK_EINVAL, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  MMDK_CUDA(cudaIpcOpenMemHandle(out_dev, h, cudaIpcMemLazyEnablePeerAccess));
+  return MMDK_OK;
+}
+int mmdk_p2p_close(void* dev) { return check_cuda(cudaIpcCloseMemHandle(dev), "cudaIpcCloseMemHandle"); }
+
 int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, int rep_index, const float* x_dev,
                        float* peers_out_dev, void* stream) {
   if (!env || !x_dev || !peers_out_dev) return fail(MMDK_EINVAL, "null argument");
   if (rep_index < 0 || rep_index >= K) return fail(MMDK_EINVAL, "rep_index out of range");
-  publish_peers_kernel<<<n_groups, 256, 0, (cudaStream_t)stream>>>(*env, K, H, rep_index, x_dev, peers_out_dev);
+  publish_peers_kernel<<<n_groups, 1024, 0, (cudaStream_t)stream>>>(*env, K, H, rep_index, x_dev, peers_out_dev);
   return check_cuda(cudaGetLastError(), "publish_peers_kernel");
 }
 
-int mmdk_build_peer_hash(const float* peers_dev, int n_peers, int H, int grid, float grid_lo, float grid_inv_cell,
-                         uint16_t* cell_start_dev, float* sorted_dev, void* stream) {
+int mmdk_build_peer_hash(const float* peers_dev, const uint32_t* seq_dev, int n_peers, int H, int grid, float grid_lo,
+                         float grid_inv_cell, uint16_t* cell_start_dev, float* sorted_dev, void* stream) {
   if (!peers_dev || !cell_start_dev || !sorted_dev) return fail(MMDK_EINVAL, "null argument");
   if (grid < 1 || grid > MMDK_PEER_GRID_MAX) return fail(MMDK_EINVAL, "peer hash grid out of range");
   if (n_peers < 1 || n_peers > 65535 || H < 1) return fail(MMDK_EINVAL, "peer hash: n_peers must be in [1, 65535]");
   const size_t smem = sizeof(int) * ((size_t)grid * grid + 1 + n_peers);
   if (smem > 48 * 1024) return fail(MMDK_EINVAL, "peer hash: fleet too large for the single-CTA-per-waypoint builder");
-  build_peer_hash_kernel<<<H, 256, smem, (cudaStream_t)stream>>>(peers_dev, n_peers, H, grid, grid_lo, grid_inv_cell,
+  build_peer_hash_kernel<<<H, 256, smem, (cudaStream_t)stream>>>(peers_dev, seq_dev, n_peers, H, grid, grid_lo, grid_inv_cell,
                                                               cell_start_dev, reinterpret_cast<float4*>(sorted_dev));
   return check_cuda(cudaGetLastError(), "build_peer_hash_kernel");
 }

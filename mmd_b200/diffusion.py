@@ -129,7 +129,7 @@ def _run_step(guide, x, hard_conds_per_group, K, eps, noise, chain_slot, sc, con
 
 
 def lower_for_step(guide, n_groups, K, H, device, hard_conds_per_group, constraints_per_group=None, peers=None,
-                   peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None):
+                   peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None, peer_seq_ptr=None):
     """(mmdk_guide_env, mmdk_groups, keepalive) for a batch of `n_groups` planner calls of K samples."""
     if guide is not None:
         env, keep = guide.lower_env(device)
@@ -141,14 +141,14 @@ def lower_for_step(guide, n_groups, K, H, device, hard_conds_per_group, constrai
         constraints_per_group = [([], [])] * n_groups
     grp, keep2 = GuideManagerTrajectoriesWithVelocity.lower_groups(
         helper, n_groups, K, H, device, constraints_per_group, hard_conds_per_group, peers, peer_self, peer_radius,
-        peer_weight, peer_hash)
+        peer_weight, peer_hash, peer_seq_ptr)
     allk = type(keep2)(list(keep) + list(keep2))
     allk.rows_d, allk.vals_d = keep2.rows_d, keep2.vals_d
     return env, grp, allk
 
 
 def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_steps=None, lockstep=False, rep_index=0,
-                     peers_local=None, use_graph=False, keep=None):
+                     peers_local=None, use_graph=False, keep=None, exchange=None):
     """One mmdk_run_chain call for a list of reverse steps.  steps: [(t_index, StepScalars)]; noise_steps / chain_steps:
     contiguous [n_steps, B, H, D] tensors (or None).  Returns the ctypes objects that must stay alive with a captured graph."""
     lib = _lib.lib()
@@ -165,6 +165,7 @@ def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_step
     desc = keep[0]
     desc.lockstep, desc.rep_index = int(bool(lockstep)), int(rep_index)
     desc.peers_local_dev = peers_local.data_ptr() if peers_local is not None else None
+    desc.exchange = C.pointer(exchange.struct) if exchange is not None else None
     B, H, D = x.shape
     if noise_steps is not None:
         assert noise_steps.is_contiguous() and noise_steps.shape[0] >= n and tuple(noise_steps.shape[1:]) == (B, H, D)

@@ -197,7 +197,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         return env, keep
 
     def lower_groups(self, n_groups, K, H, device, constraints_per_group, hard_conds_per_group, peers=None,
-                     peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None):
+                     peer_self=None, peer_radius=0.0, peer_weight=0.0, peer_hash=None, peer_seq_ptr=None):
         """mmdk_groups for `n_groups` planner calls of K samples.  constraints_per_group[g] = (costs, weights);
         hard_conds_per_group[g] = {row: tensor[D]} (normalised) or None."""
         grp = _lib.Groups()
@@ -246,6 +246,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
             keep += [peers, peer_self]
             grp.peers_dev, grp.peer_self_dev = peers.data_ptr(), peer_self.data_ptr()
             grp.n_peers = peers.shape[0]
+            grp.peer_seq_dev = peer_seq_ptr   # not None: `peers` is half 0 of a double-buffered exchange table
             grp.peer_radius, grp.peer_weight = float(peer_radius), float(peer_weight)
             if peer_hash is not None:
                 keep.append(peer_hash)
@@ -258,6 +259,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
                 grp.peer_sorted_dev = None
         else:
             grp.peers_dev = None
+            grp.peer_seq_dev = None
             grp.n_peers = 0
             grp.peer_cell_start_dev = None
             grp.peer_sorted_dev = None
@@ -283,7 +285,7 @@ class PeerHash:
 
     def build(self, peers):
         assert peers.shape == (self.n_peers, self.H, 2) and peers.is_contiguous()
-        _lib.check(_lib.lib().mmdk_build_peer_hash(_lib.ptr(peers), self.n_peers, self.H, self.grid, self.lo,
+        _lib.check(_lib.lib().mmdk_build_peer_hash(_lib.ptr(peers), None, self.n_peers, self.H, self.grid, self.lo,
                                                    self.inv_cell, _lib.ptr(self.cell_start), _lib.ptr(self.sorted),
                                                    _lib.stream_ptr()))
         return self

@@ -51,7 +51,7 @@ def gather_peers(peers_local: torch.Tensor, n_robots_total: int, group=None) -> 
 class MultiRobotSampler:
     def __init__(self, model: GaussianDiffusionModel, guide, n_guide_steps=20, t_start_guide=None, noise_std=0.5,
                  n_diffusion_steps_without_noise=1, peer_radius=2.4 * 0.05, peer_weight=2e-2, rep_index=0,
-                 process_group=None, use_peer_hash=True, use_graph=True):
+                 process_group=None, use_peer_hash="auto", use_graph=True, exchange="p2p"):
         self.model, self.guide = model, guide
         self.n_guide_steps = n_guide_steps
         T = model.n_diffusion_steps
@@ -60,8 +60,14 @@ class MultiRobotSampler:
         self.n_extra = n_diffusion_steps_without_noise
         self.peer_radius, self.peer_weight, self.rep_index = peer_radius, peer_weight, rep_index
         self.pg = process_group
-        self.use_peer_hash = use_peer_hash  # False: brute-force scan of the peer table (kept for the equality test)
-        self.use_graph = use_graph          # single-process chains: capture the step loop once, replay (mmdk_run_chain)
+        # peer term: spatial hash (O(neighbours)) or brute-force scan of the staged table; "auto" = hash for fleets > 64 robots
+        # (measured on B200: at 32 robots the scan executes fewer instructions than the 3x3-cell walk)
+        self.use_peer_hash = use_peer_hash
+        self.use_graph = use_graph          # capture the step loop once, replay (mmdk_run_chain)
+        # lock-step exchange: "p2p" = publication fused into the step kernel over peer memory (mmd_b200/exchange.py; also
+        # across processes -> one graph per rank); "nccl" = host loop with one all-gather per guided step (fallback, A/B);
+        # None = separate publish kernel, single process only
+        self.exchange = exchange
         self._ws = {}
 
     # -- persistent buffers: stable device pointers let mmdk_run_chain replay its captured CUDA graph -------------------
@@ -72,11 +78,27 @@ class MultiRobotSampler:
                 self._ws.pop(next(iter(self._ws)))
             ws = dict(x=torch.empty(B, H, D, device=dev), eps=torch.empty(B, H, D, device=dev), noise=None,
                       chain=torch.empty(n_steps + 1, B, H, D, device=dev) if return_chain else None,
-                      peers=None, peer_self=None, peer_hash=None, lowered=None, keep=None, hc_sig=None)
+                      peers=None, peer_self=None, peer_hash=None, lowered=None, keep=None, hc_sig=None, ex=None)
             if mode == "lockstep":
-                ws["peers"] = torch.zeros(R_total, H, 2, device=dev)
+                distributed = R_total != R
+                use_ex = self.exchange == "p2p" and R_total > 1
+                if use_ex:
+                    from .exchange import PeerExchange
+                    try:
+                        ws["ex"] = PeerExchange(R_total, H, robot_offset, self.rep_index, dev, group=self.pg,
+                                                distributed=distributed)
+                    except _lib.MMDKError as e:   # CUDA IPC unavailable (e.g. no peer access): NCCL all-gather loop instead
+                        if not distributed:
+                            raise
+                        import warnings
+                        warnings.warn(f"peer-memory exchange unavailable ({e}); using the NCCL all-gather loop")
+                if ws["ex"] is not None:
+                    ws["peers"] = ws["ex"].table[0]
+                else:
+                    ws["peers"] = torch.zeros(R_total, H, 2, device=dev)
                 ws["peer_self"] = torch.arange(robot_offset, robot_offset + R, dtype=torch.int32, device=dev)
-                if self.use_peer_hash and R_total > 1:
+                hash_on = (R_total > 64) if self.use_peer_hash == "auto" else bool(self.use_peer_hash)
+                if hash_on and R_total > 1:
                     ws["peer_hash"] = PeerHash(R_total, H, self.peer_radius, dev)
             self._ws[key] = ws
         return ws
@@ -144,7 +166,8 @@ class MultiRobotSampler:
         hc_sig = tuple(tuple(sorted(int(r) for r in hc)) for hc in hard_conds_l)
         if ws["lowered"] is None or has_constraints or ws["hc_sig"] != hc_sig:
             ws["lowered"] = lower_for_step(guide, R, K, H, dev, list(hard_conds_l), list(constraints_l), ws["peers"],
-                                           ws["peer_self"], self.peer_radius, self.peer_weight, ws["peer_hash"])
+                                           ws["peer_self"], self.peer_radius, self.peer_weight, ws["peer_hash"],
+                                           ws["ex"].seq_ptr if ws["ex"] is not None else None)
             ws["hc_sig"] = hc_sig
             ws["keep"] = None
         else:
@@ -157,14 +180,16 @@ class MultiRobotSampler:
             steps.append((max(i, 0), model.step_scalars(i, self.n_guide_steps if guided else 0, self.noise_std, True), guided))
 
         lock = mode == "lockstep" and R_total > 1
-        if not (distributed and lock):
-            # one native call for the whole chain (graph replay when the pointers are the persistent ones)
+        if not (distributed and lock) or ws["ex"] is not None:
+            # one native call for the whole chain (graph replay when the pointers are the persistent ones); with the
+            # peer-memory exchange this also covers a fleet sharded over processes
             from .diffusion import run_chain_native
             graph_ok = self.use_graph and not has_constraints
-            peers_local = ws["peers"][robot_offset:robot_offset + R] if lock else None
+            peers_local = ws["peers"][robot_offset:robot_offset + R] if (lock and ws["ex"] is None) else None
             ws["keep"] = run_chain_native(model, ws["lowered"], [(t, sc) for t, sc, _ in steps], x, eps, nz_all,
                                           chain[1:] if return_chain else None, lockstep=lock, rep_index=self.rep_index,
-                                          peers_local=peers_local, use_graph=graph_ok, keep=ws["keep"])
+                                          peers_local=peers_local, use_graph=graph_ok, keep=ws["keep"],
+                                          exchange=ws["ex"] if lock else None)
         else:
             # fleet sharded over processes: the representative paths are exchanged between publication and hash build
             peers = ws["peers"]

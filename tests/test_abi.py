@@ -26,7 +26,7 @@ def test_struct_layouts_match_header_field_order():
     src = open(os.path.join(ROOT, "include", "mmdk.h")).read()
     for cname, struct in [("mmdk_step_scalars", _lib.StepScalars), ("mmdk_groups", _lib.Groups),
                           ("mmdk_guide_env", _lib.GuideEnv), ("mmdk_unet_config", _lib.UnetConfig),
-                          ("mmdk_chain_desc", _lib.ChainDesc)]:
+                          ("mmdk_chain_desc", _lib.ChainDesc), ("mmdk_peer_exchange", _lib.PeerExchange)]:
         end = src.index("} " + cname + ";")
         body = src[src.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header_field_order():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int|void|uint16_t|uint8_t|int64_t|int32_t|mmdk_step_scalars)\s*\*?\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int|void|uint16_t|uint8_t|uint32_t|int64_t|int32_t|mmdk_step_scalars|mmdk_peer_exchange)\s*\*?\s*", "", decl)
             for f in decl.split(","):
                 fields.append(re.sub(r"\[.*\]", "", f).strip().lstrip("*").strip())
         assert fields == [f[0] for f in struct._fields_], cname
