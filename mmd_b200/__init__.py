@@ -11,7 +11,8 @@ from .guides import GuideManagerTrajectoriesWithVelocity  # noqa: F401
 from .costs import CostCollision, CostComposite, CostConstraint, CostGPTrajectory  # noqa: F401
 from .tasks import PlanningTask, RobotPlanarDisk  # noqa: F401
 from .datasets import LimitsNormalizer, TrajectoryDataset  # noqa: F401
-from .sampler import MultiRobotSampler  # noqa: F401
+from .sampler import MultiRobotSampler, shard_robots, gather_peers  # noqa: F401
+from .exchange import PeerExchange  # noqa: F401
 from .planners import MPD, DiffusionsEnsemble, MultiPointConstraint, PlannerOutput  # noqa: F401
 from . import envs  # noqa: F401
 from . import conflicts, smoothing  # noqa: F401
