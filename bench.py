@@ -407,8 +407,17 @@ def planner_bench(M, model, env_name, ta, starts, goals, K, n_calls):
         n_free += 0 if out.trajs_final_free is None else int(out.trajs_final_free.shape[0])
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    # the same calls served in one batch (mmd_b200.plan_batch: bit-identical results to the sequential calls)
+    M.plan_batch(planners)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    M.plan_batch(planners)
+    torch.cuda.synchronize()
+    dt_b = time.perf_counter() - t0
     return {"value": n_calls * K / dt, "unit": "trajectories/s", "calls": n_calls, "ms_per_call": 1e3 * dt / n_calls,
             "collision_free_trajectories": n_free,
+            "batched": {"value": n_calls * K / dt_b, "unit": "trajectories/s", "ms_total": 1e3 * dt_b,
+                        "note": "mmd_b200.plan_batch(planners): the same planner calls as ONE batched chain + per-planner post-processing"},
             "note": "sequential MPD.__call__(start, goal) -> PlannerOutput, K samples each, no inter-robot constraints (CBS root "
                     "calls), host wall clock including the planner's post-processing (unnormalise the chain, collision "
                     "classification, best-trajectory selection, Savitzky-Golay smoothing)"}

@@ -13,7 +13,8 @@ from .tasks import PlanningTask, RobotPlanarDisk  # noqa: F401
 from .datasets import LimitsNormalizer, TrajectoryDataset  # noqa: F401
 from .sampler import MultiRobotSampler, shard_robots, gather_peers  # noqa: F401
 from .exchange import PeerExchange  # noqa: F401
-from .planners import MPD, DiffusionsEnsemble, MultiPointConstraint, PlannerOutput  # noqa: F401
+from .planners import (MPD, MPDEnsemble, plan_batch, DiffusionsEnsemble, MultiPointConstraint, PlannerOutput,  # noqa: F401
+                       PlanningTaskEnsemble)
 from . import envs  # noqa: F401
 from . import conflicts, smoothing  # noqa: F401
 from .conflicts import get_conflicts, count_conflicts_batched, global_pad_paths  # noqa: F401

@@ -62,15 +62,18 @@ __global__ void conflicts_kernel(const float* __restrict__ base, const float* __
 // linear operator S [H, H] (built by the host in float64, mmd_b200/smoothing.py); accumulation in double, result fp32.
 __global__ void smooth_kernel(const double* __restrict__ S, const float* __restrict__ x, int B, int H, int D,
                               float* __restrict__ y) {
-  extern __shared__ double s_S[];   // [H][H]
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) s_S[i] = S[i];
-  __syncthreads();
+  extern __shared__ double s_S[];   // [H][H] when it fits (H <= 72); longer horizons (multi-tile paths) read S through L2
+  const bool staged = H <= 72;
+  if (staged) {
+    for (int i = threadIdx.x; i < H * H; i += blockDim.x) s_S[i] = S[i];
+    __syncthreads();
+  }
   const int per = H * D;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)B * per; idx += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(idx / per), r = (int)(idx - (int64_t)b * per);
     const int h = r / D, d = r - h * D;
     const float* xb = x + (size_t)b * per + d;
-    const double* row = s_S + (size_t)h * H;
+    const double* row = (staged ? s_S : S) + (size_t)h * H;
     double acc = 0.0;
     for (int j = 0; j < H; ++j) acc += row[j] * (double)xb[(size_t)j * D];
     y[idx] = (float)acc;
@@ -102,10 +105,10 @@ int mmdk_get_conflicts(const float* base_paths_dev, const float* cand_paths_dev,
 int mmdk_smooth_trajs(const double* filter_dev, const float* trajs_dev, int B, int H, int D, float* out_dev, void* stream) {
   if (!filter_dev || !trajs_dev || !out_dev) return fail(MMDK_EINVAL, "null argument");
   if (B <= 0) return MMDK_OK;
-  if (H < 1 || H > 72 || D < 1) return fail(MMDK_EINVAL, "horizon must be in [1, 72]");   // H*H doubles in 48 KB of shared memory
+  if (H < 1 || H > 4096 || D < 1) return fail(MMDK_EINVAL, "horizon must be in [1, 4096]");
   const int64_t n = (int64_t)B * H * D;
   const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-  smooth_kernel<<<grid, 256, sizeof(double) * H * H, (cudaStream_t)stream>>>(filter_dev, trajs_dev, B, H, D, out_dev);
+  smooth_kernel<<<grid, 256, H <= 72 ? sizeof(double) * H * H : 0, (cudaStream_t)stream>>>(filter_dev, trajs_dev, B, H, D, out_dev);
   return check_cuda(cudaGetLastError(), "smooth_kernel");
 }
 

@@ -77,7 +77,16 @@ def _t_int(t):
 
 def _hard_rows(hard_conds):
     """{row: [B, D] or [D]} -> {row: [D]} (run_inference repeats one state over the batch, :327-329)."""
-    return {k: (v[0] if torch.is_tensor(v) and v.dim() == 2 else v) for k, v in (hard_conds or {}).items()}
+    out = {}
+    for k, v in (hard_conds or {}).items():
+        if torch.is_tensor(v) and v.dim() == 2:
+            # a planner call shares ONE state per conditioned waypoint (the kernel's group layout); per-sample conditions
+            # would be silently dropped otherwise
+            if v.shape[0] > 1 and not bool((v == v[0:1]).all()):
+                raise ValueError("per-sample hard conditions are not supported: all rows of a [B, D] condition must be equal")
+            v = v[0]
+        out[k] = v
+    return out
 
 
 @torch.no_grad()

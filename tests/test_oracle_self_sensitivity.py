@@ -11,7 +11,9 @@ output is multiplied by (1 + delta * N(0,1)):
     constraint radius, the normaliser's global clip -- amplified by the clipped GP steps of the same timestep).
 The GPU tests therefore assert medians and bounded outlier FRACTIONS, not a hard per-pair maximum."""
 import math
+import os
 
+import pytest
 import torch
 
 from oracle import port
@@ -77,3 +79,20 @@ def test_teacher_forced_steps_have_isolated_outliers():
               f"{int((guided > 1e-3).sum())} of {guided.numel()} ({100 * frac:.2f}%)")
         assert float(e.median()) < 1e-4
         assert frac < 0.05
+
+
+@pytest.mark.skipif(os.environ.get("MMD_SLOW") != "1", reason="minutes of CPU time: set MMD_SLOW=1")
+def test_free_running_k128():
+    """The percentile the GPU test test_run_inference_chain_free_running_tensor_core[128] is held to.  Measured (16 cores):
+    delta 1e-7: median 7.29e-07 p90 2.10e-04 max 2.20e-02, 92.2% below 1e-3; 1.3e-6: 1.02e-06 / 3.86e-05 / 9.68e-03, 93.8%;
+    3e-6: 1.86e-06 / 1.72e-04 / 2.18e-02, 93.0%."""
+    K, T = 128, 100
+    for delta in (1e-7, 1.3e-6, 3e-6):
+        o, pert, noise, hc = _problem(K, T, 0.0, delta)
+        ref = port.run_inference(o["model"], hc, K, noise, guide=o["guide"])
+        alt = port.run_inference(pert, hc, K, noise, guide=o["guide"])
+        e = _per_traj(alt[-1], ref[-1])
+        frac = float((e < 1e-3).float().mean())
+        print(f"oracle self-sensitivity free running K=128 T=100 GP off delta={delta:.1e}: median {float(e.median()):.2e} "
+              f"p90 {float(e.quantile(0.9)):.2e} max {float(e.max()):.2e}, {100 * frac:.1f}% below 1e-3")
+        assert 0.85 < frac < 0.99

@@ -137,3 +137,52 @@ def test_smooth_trajs_matches_reference():
     from mmd.common.trajectory_utils import smooth_trajs
     x = torch.randn(6, 64, 4, generator=torch.Generator().manual_seed(1))
     assert torch.equal(smooth_trajs(x), port.smooth_trajs(x))
+
+
+@pytest.mark.parametrize("env_name", ["EnvHighways2D", "EnvEmpty2D", "EnvConveyor2D"])
+def test_reference_cost_objects_lower_like_ours(env_name):
+    """INTEGRATION.md section A claims the reference's OWN CostComposite / CostCollision / CostGPTrajectory /
+    CostConstraint / PlanningTask objects lower by duck typing.  Build them with the live reference, hand them to
+    mmd_b200's GuideManagerTrajectoriesWithVelocity and compare the lowered mmdk_guide_env (every scalar field and the
+    packed SDF grid, bit for bit) and the bucketed constraint arrays with the lowering of mmd_b200's own objects."""
+    import ctypes as C
+    from oracle import ref_build
+    import mmd_b200 as M
+    from mmd_b200 import _lib
+    from mmd_b200.guides import ConstraintSet
+    r = ref_build.build_reference(env_name, 25, None, with_model=False)
+    cpu = torch.device("cpu")
+    g_ref = M.GuideManagerTrajectoriesWithVelocity(r["dataset"], r["guide"].cost, clip_grad=True, tensor_args=r["tensor_args"])
+    ta = {"device": cpu, "dtype": torch.float32}
+    env = M.envs.get_env(env_name + "ExtraObjects", tensor_args=ta)
+    robot = M.RobotPlanarDisk(tensor_args=ta)
+    task = M.PlanningTask(env=env, robot=robot, ws_limits=env.limits, obstacle_cutoff_margin=0.05, tensor_args=ta)
+    dataset = M.TrajectoryDataset(env, robot, task, *port.DEFAULT_NORMALIZER_LIMITS, tensor_args=ta)
+    costs = [M.CostCollision(robot, 64, field=f, sigma_coll=1.0, tensor_args=ta) for f in task.get_collision_fields()]
+    costs.append(M.CostGPTrajectory(robot, 64, 5.0 / 64, sigma_gp=1.0, tensor_args=ta))
+    comp = M.CostComposite(robot, 64, costs, weights_cost_l=[2e-2] * (len(costs) - 1) + [8e-2], tensor_args=ta)
+    g_own = M.GuideManagerTrajectoriesWithVelocity(dataset, comp, clip_grad=True, tensor_args=ta)
+    e_ref, keep_ref = g_ref.lower_env(cpu)
+    e_own, keep_own = g_own.lower_env(cpu)
+    for name, ctype in _lib.GuideEnv._fields_:
+        if name == "grid_dev":
+            continue
+        a, b = getattr(e_ref, name), getattr(e_own, name)
+        a = list(a) if hasattr(a, "__len__") else a
+        b = list(b) if hasattr(b, "__len__") else b
+        assert a == b, (name, a, b)
+    assert (e_ref.grid_dev is None) == (e_own.grid_dev is None)
+    grids_ref = [k for k in keep_ref if torch.is_tensor(k) and k.dim() == 3]
+    grids_own = [k for k in keep_own if torch.is_tensor(k) and k.dim() == 3]
+    assert len(grids_ref) == len(grids_own)
+    for a, b in zip(grids_ref, grids_own):
+        assert torch.equal(a, b)
+    # CostConstraint objects of the reference -> the same bucketed arrays
+    qs = torch.rand(30, 2, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    hh = torch.randint(0, 60, (30,), generator=torch.Generator().manual_seed(2)).float()
+    rng = torch.stack((hh, hh + 3), -1)
+    rad = torch.full((30,), 0.12)
+    cc_ref = ref_build.make_cost_constraint(r, qs, rng, rad, True)
+    cc_own = M.CostConstraint(robot, 64, q_l=list(qs), traj_range_l=rng.tolist(), radius_l=rad.tolist(), is_soft=True, tensor_args=ta)
+    s_ref, s_own = ConstraintSet([cc_ref], [2e-2], 64, cpu), ConstraintSet([cc_own], [2e-2], 64, cpu)
+    assert torch.equal(s_ref.bucket_ptr, s_own.bucket_ptr) and torch.equal(s_ref.cons, s_own.cons)
