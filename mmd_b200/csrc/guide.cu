@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
         *reinterpret_cast<float4*>(r) = make_float4(gk[0], gk[1], gk[2], gk[3]);
       }
       ++tap;
-      clip_by_norm(gk, E.max_grad_norm);
+      // clip_by_norm of an all-zero gradient is exactly zero (ratio = clip(2e-6, 0, max) / 2e-6 is finite and positive):
+      // most waypoints are neither in collision nor near a constraint, so skip the sqrt / division for them
+      if (gk[0] != 0.f || gk[1] != 0.f || gk[2] != 0.f || gk[3] != 0.f) clip_by_norm(gk, E.max_grad_norm);
       if (!interior) { gk[0] = gk[1] = gk[2] = gk[3] = 0.f; }   // guides.py:216-218
 #pragma unroll
       for (int d = 0; d < 4; ++d) acc[d] = acc[d] + w * gk[d];
@@ -350,15 +352,28 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
         }
       } else {
         const float2* pq = (a.peers_in_smem ? s_peers : reinterpret_cast<const float2*>(a.grp.peers_dev) + peer_half) + h;
-#pragma unroll 4
-        for (int j = 0; j < a.grp.n_peers; ++j, pq += H) {
-          if (j == self_peer) continue;
-          const float2 q = *pq;
-          float dx = xu[0] - q.x, dy = xu[1] - q.y;
-          float d2 = dx * dx + dy * dy;
-          if (d2 > r2_far) continue;   // surely outside the radius; the exact test below handles the boundary
-          float dist = sqrtf(d2);
-          if (!(dist > r) && dist > 0.f) { const float inv = 1.f / dist; gk[0] -= dx * inv; gk[1] -= dy * inv; }
+        // two passes over blocks of 32 peers: (1) branch-free squared-distance prefilter into a bit mask (in-radius peers are
+        // rare), (2) the exact reference test (sqrt, dist <= r) and the accumulation for the set bits only, in ascending peer
+        // order -- the same peers contribute in the same order as a plain scan
+        for (int j0 = 0; j0 < a.grp.n_peers; j0 += 32) {
+          const int nb = min(32, a.grp.n_peers - j0);
+          unsigned mask = 0u;
+#pragma unroll 8
+          for (int jj = 0; jj < nb; ++jj) {
+            const float2 q = pq[(size_t)(j0 + jj) * H];
+            const float dx = xu[0] - q.x, dy = xu[1] - q.y;
+            const float d2 = dx * dx + dy * dy;
+            mask |= (d2 > r2_far) ? 0u : (1u << jj);   // surely outside the radius otherwise
+          }
+          if (self_peer >= j0 && self_peer < j0 + 32) mask &= ~(1u << (self_peer - j0));
+          while (mask) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float2 q = pq[(size_t)(j0 + jj) * H];
+            const float dx = xu[0] - q.x, dy = xu[1] - q.y;
+            const float dist = sqrtf(dx * dx + dy * dy);
+            if (!(dist > r) && dist > 0.f) { const float inv = 1.f / dist; gk[0] -= dx * inv; gk[1] -= dy * inv; }
+          }
         }
       }
       emit(gk, a.grp.peer_weight);
