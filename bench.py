@@ -289,7 +289,8 @@ def run_gpu(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     if fused:
-        grid = min((B + 6) // 7, n_sm)
+        spt = 1 if B <= n_sm else (3 if B <= 3 * n_sm else 7)   # samples per tile the executor picks (unet_fused.cu build_fused)
+        grid = min((B + spt - 1) // spt, n_sm)
         st = stamps[:, :grid].cpu()
         live = (st[:, :, 0] > 0).all(dim=1) & (st[:, :, 1] > 0).all(dim=1)
         dur_ns = (st[:, :, 1].max(dim=1).values - st[:, :, 0].min(dim=1).values)[live].double()

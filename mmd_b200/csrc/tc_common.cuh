@@ -10,7 +10,7 @@
 namespace mmdk {
 namespace {
 
-constexpr int ST = 7;          // samples per tile
+constexpr int ST = 7;          // samples per tile (per-layer executor; the persistent executor picks 7 / 3 / 1 per batch size)
 constexpr int MAX_W_STAGES = 3;
 constexpr int TC_THREADS = 320;
 constexpr int TMEM_COLS = 256;
@@ -160,6 +160,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -236,11 +242,11 @@ static __global__ void pack_wchunk_kernel(const float* __restrict__ W, int cin, 
 
 // network input x [B][L][D] fp32 -> level-0 image with C = 16 (channels D..15 stay zero)
 static __global__ void pack_input_kernel(const float* __restrict__ x, int B, int L, int D, int rows, uint8_t* __restrict__ img,
-                                  uint32_t tile_bytes) {
+                                  uint32_t tile_bytes, int st = ST) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * L) return;
   const int b = idx / L, pos = idx - b * L;
-  const int tile = b / ST, s = b - tile * ST;
+  const int tile = b / st, s = b - tile * st;
   const int r = 2 + s * (L + 2) + pos;
   float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int d = 0; d < D && d < 8; ++d) y[d] = x[(size_t)idx * D + d];
@@ -253,11 +259,11 @@ static __global__ void pack_input_kernel(const float* __restrict__ x, int B, int
 
 // debug tap: image -> fp32 [B][C][L]
 static __global__ void unpack_image_kernel(const uint8_t* __restrict__ img, uint32_t tile_bytes, int B, int C, int L, int rows,
-                                    float* __restrict__ out) {
+                                    float* __restrict__ out, int st = ST) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C * L) return;
   const int pos = idx % L, c = (idx / L) % C, b = idx / (L * C);
-  const int tile = b / ST, s = b - tile * ST;
+  const int tile = b / st, s = b - tile * st;
   const int r = 2 + s * (L + 2) + pos;
   const __half* base = reinterpret_cast<const __half*>(img + (size_t)tile * tile_bytes);
   const size_t o = ((size_t)(c >> 3) * rows + r) * 8 + (c & 7);
@@ -267,7 +273,7 @@ static __global__ void unpack_image_kernel(const uint8_t* __restrict__ img, uint
 
 
 
-inline int level_rows(int L) { return 2 + 128 * ((ST * (L + 2) + 127) / 128) + 2; }
+inline int level_rows(int L, int st = ST) { return 2 + 128 * ((st * (L + 2) + 127) / 128) + 2; }
 
 }  // namespace
 

@@ -45,7 +45,7 @@ constexpr int F_PART_ROWS = 512;
 constexpr int F_MAX_N = 128;
 
 // epilogue variants of the conv block: (m-tiles per image, columns per m-tile)
-enum FVariant : int { FV_4_32 = 0, FV_2_64 = 1, FV_1_128 = 2, FV_2_32 = 3, FV_1_64 = 4, FV_GENERIC = 5 };
+enum FVariant : int { FV_4_32 = 0, FV_2_64 = 1, FV_1_128 = 2, FV_2_32 = 3, FV_1_64 = 4, FV_GENERIC = 5, FV_1_32 = 6 };
 
 struct FOp {
   int kind, L, P, n_mt, N, cout, variant;
@@ -98,6 +98,7 @@ constexpr int F_MAX_OPS = 40, F_MAX_CHUNKS = 448;
 // ~120 cycles per tcgen05.mma).
 struct FParams {
   int n_ops, n_tiles, B;
+  int st;                     // samples per tile: 7, or 3 / 1 for batches that then still fit one tile per SM (build_fused)
   int by_slot;                // 1: intermediate images are indexed by (CTA, parity) slot (L2-resident footprint), 0: by tile
   const float* cond_row;
   float* eps;
@@ -130,7 +131,8 @@ template <int NH>
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
   if constexpr (NH == 32) tmem_ld32(taddr, v);
   else if constexpr (NH == 16) tmem_ld16(taddr, v);
-  else tmem_ld8(taddr, v);
+  else if constexpr (NH == 8) tmem_ld8(taddr, v);
+  else tmem_ld4(taddr, v);
 }
 
 __device__ __forceinline__ uint4 ld_cg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
@@ -147,7 +149,7 @@ struct EpiCtx {
   float2* stat;      // [ST * 8] (-mean * rstd, rstd) of this item
   uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
   uint8_t* sbuf;     // the parity's input buffer (shared memory), target of the in-place output
-  int tile, img, B;
+  int tile, img, B, st;   // st = samples per tile of this launch
   long long* dbg;    // this item's stamp row (CTA 0, thread 0 only) or nullptr
 };
 
@@ -223,7 +225,7 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     for (int i = 0; i < NMT; ++i) {
       const int q = 128 * i + c.row;
       const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
-      const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+      const bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
       uint8_t* obase = op->out2 + (size_t)c.img * op->out2_tile_bytes + (size_t)(2 + q) * 16;
 #pragma unroll 1
       for (int pc = 0; pc < NP; ++pc) {
@@ -274,7 +276,7 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
     const int q = 128 * i + c.row;
     siv[i] = (int)(((uint32_t)q * pinv) >> 16);
     const int pi = q - siv[i] * Pp;
-    okv[i] = (siv[i] < ST) && (pi < L) && (c.tile * ST + siv[i] < c.B);
+    okv[i] = (siv[i] < c.st) && (pi < L) && (c.tile * c.st + siv[i] < c.B);
   }
   uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
   if (rimg && okv[0]) {
@@ -335,7 +337,7 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
   epi_bar16();
   if (c.dbg) c.dbg[10] = clock64();
   // ---- Chan combination: 8 threads per (sample, group), partials read ONCE into registers --------------------------------
-  if (c.tid < ST * 8 * 8) {
+  if (c.tid < c.st * 8 * 8) {
     const int pair = c.tid >> 3, sub = c.tid & 7;
     const int s = pair >> 3, g = pair & 7;
     const float2* pg = c.part + g * F_PART_ROWS + s * Pp;
@@ -438,12 +440,12 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
       for (int i = 0; i < NMT; ++i) {
         const int q = 128 * i + c.row;
         const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
-        const bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+        const bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
         float y[8];
         tmem_ld8(lane_base + i * N, y);
         tmem_wait_ld();
         if (ok) {
-          const size_t b = (size_t)c.tile * ST + si;
+          const size_t b = (size_t)c.tile * c.st + si;
           *reinterpret_cast<float4*>(eps + (b * L + pi) * 4) =
               make_float4(y[0] + c.p_bias[0], y[1] + c.p_bias[1], y[2] + c.p_bias[2], y[3] + c.p_bias[3]);
         }
@@ -460,7 +462,7 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
       for (int i = 0; i < NMT; ++i) {
         const int q = 128 * i + c.row;
         const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
-        bool ok = (si < ST) && (pi < L) && (c.tile * ST + si < c.B);
+        bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
         int ro;
         if (op->kind == TC_DOWN) {   // stride-2 conv evaluated at every position; keep the even ones
           ok = ok && ((pi & 1) == 0);
@@ -709,6 +711,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
     c.tid = tid; c.warp = warp; c.lane = lane; c.q4 = warp & 3; c.cb = warp >> 2; c.row = c.q4 * 32 + lane;
     c.part = reinterpret_cast<float2*>(smem + P.off_part);
     c.B = P.B;
+    c.st = P.st;
     int k = 0, nuse0 = 0, nuse1 = 0;
     F_FOR_ITEMS {
       const FOp* op = &P.ops[j];
@@ -739,6 +742,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
           case FV_2_64: epi_convblock<2, 64>(op, c, bae); break;
           case FV_1_128: epi_convblock<1, 128>(op, c, bae); break;
           case FV_2_32: epi_convblock<2, 32>(op, c, bae); break;
+          case FV_1_32: epi_convblock<1, 32>(op, c, bae); break;
           default: epi_convblock<1, 64>(op, c, bae); break;
         }
       } else {
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
 // host
 // ------------------------------------------------------------------------------------------------------------------
 struct FusedState {
-  int B = 0, n_tiles = 0, grid = 0, by_slot = 0;
+  int B = 0, n_tiles = 0, grid = 0, by_slot = 0, st = ST;
   bool keep_all = false;           // every activation image also goes to global memory (debug taps)
   std::vector<TcImage> images;     // [0] = packed network input, [1 + j] = output of op j
   std::vector<TcImage> images_r;   // [j] = residual-conv image written by op j (dev == nullptr if none)
@@ -808,7 +812,15 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   MMDK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   auto* st = new FusedState();
   st->B = B;
-  st->n_tiles = (B + ST - 1) / ST;
+  // samples per tile.  Measured kernel durations on B200 (tests/tc_stamps.py): a lone tile's 30-op chain costs 196 us with 1
+  // sample, 204 us with 3, 255 us with 7 (the C=128 / L=16 layers sweep a full M=128 tile whatever it holds), so smaller tiles
+  // only pay while they still fit one per SM.  MMDK_FUSED_ST overrides (A/B runs).
+  {
+    int spt = (B <= n_sm) ? 1 : ((B <= 3 * n_sm) ? 3 : 7);
+    if (const char* e = getenv("MMDK_FUSED_ST")) { const int v = atoi(e); if (v == 7 || v == 3 || v == 1) spt = v; }
+    st->st = spt;
+  }
+  st->n_tiles = (B + st->st - 1) / st->st;
   st->grid = std::min(st->n_tiles, n_sm);
   st->by_slot = by_slot;
   st->keep_all = keep_all;
@@ -820,7 +832,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   auto fail_free = [&](const std::string& m) { fused_free(st); return fail(MMDK_EINVAL, m); };
 
   auto make_image = [&](TcImage& im, int C, int L, int entries) -> int {
-    im.C = C; im.L = L; im.rows = level_rows(L);
+    im.C = C; im.L = L; im.rows = level_rows(L, st->st);
     im.tile_bytes = (uint32_t)C * im.rows * 4;
     const size_t bytes = (size_t)im.tile_bytes * entries;
     if (cudaMalloc(&im.dev, bytes) != cudaSuccess) return MMDK_ENOMEM;
@@ -845,7 +857,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
     p = FOp{};
     p.kind = op.type == OP_CONVBLOCK ? TC_CONVBLOCK : op.type == OP_DOWN ? TC_DOWN : op.type == OP_UP ? TC_UP : TC_FINAL;
     p.L = op.lin; p.P = op.lin + 2;
-    const int rows = level_rows(op.lin);
+    const int rows = level_rows(op.lin, st->st);
     p.n_mt = (rows - 4) / 128;
     p.cout = op.cout;
     p.N = op.cout < 16 ? 16 : op.cout;
@@ -861,6 +873,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
       else if (p.n_mt == 1 && p.N == 128) p.variant = FV_1_128;
       else if (p.n_mt == 2 && p.N == 32) p.variant = FV_2_32;
       else if (p.n_mt == 1 && p.N == 64) p.variant = FV_1_64;
+      else if (p.n_mt == 1 && p.N == 32) p.variant = FV_1_32;
       else return fail_free("tensor-core executor: unsupported conv block shape");
     } else if (p.kind != TC_FINAL && p.N < 32) {
       return fail_free("tensor-core executor: resampling convs need >= 32 channels");
@@ -1043,6 +1056,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   P.n_ops = n_ops;
   P.n_tiles = st->n_tiles;
   P.B = B;
+  P.st = st->st;
   P.by_slot = by_slot;
   *out = st;
   return MMDK_OK;
@@ -1087,7 +1101,7 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
   {
     const TcImage& im = st->images[0];
     const int n = B * cfg.horizon;
-    pack_input_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, B, cfg.horizon, cfg.state_dim, im.rows, im.dev, im.tile_bytes);
+    pack_input_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, B, cfg.horizon, cfg.state_dim, im.rows, im.dev, im.tile_bytes, st->st);
   }
   FParams& P = st->prm;   // ~16 KB: patched in place, copied once by the launch
   P.cond_row = net->cond_table + (size_t)t * net->n_cond;
@@ -1115,7 +1129,7 @@ int unet_fused_tap(UnetImpl* net, int op_index, float* out, int* c_out, int* l_o
   if (l_out) *l_out = im.L;
   if (!out) return MMDK_OK;
   const int n = st->B * im.C * im.L;
-  unpack_image_kernel<<<(n + 255) / 256, 256, 0, stream>>>(im.dev, im.tile_bytes, st->B, im.C, im.L, im.rows, out);
+  unpack_image_kernel<<<(n + 255) / 256, 256, 0, stream>>>(im.dev, im.tile_bytes, st->B, im.C, im.L, im.rows, out, st->st);
   return check_cuda(cudaGetLastError(), "unpack_image_kernel");
 }
 

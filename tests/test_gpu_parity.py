@@ -55,10 +55,11 @@ def test_unet_fp32_matches_oracle(pair, dev, B):
         assert e < 2e-5
 
 
-@pytest.mark.parametrize("B", [3, 7, 20])
+@pytest.mark.parametrize("B", [3, 7, 20, 200, 1100])
 def test_unet_tensor_core_matches_oracle(pair, dev, B):
     """tcgen05 executor (FP16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM): every layer op through the debug tap,
-    then eps.  Expected ~2e-6 (CPU emulation of the operand format); bar 5e-5."""
+    then eps.  Expected ~2e-6 (CPU emulation of the operand format); bar 5e-5.  The batch sizes cover
+    the three tilings of the persistent executor: 1 sample per tile (B <= 148), 3 (B <= 444) and 7."""
     import ctypes as C
     from mmd_b200 import _lib
     o, p = pair
