@@ -134,7 +134,11 @@ class TemporalUnet(nn.Module):
         self._handle = None
         self._handle_key = None
         self._keepalive = None
+        self._plist = None
         self._time_table_steps = 1024
+        # a load_state_dict through ANY ancestor module reaches this hook (nn.Module.load_state_dict runs the post hooks of
+        # every module it visits), including assign=True loads that replace the Parameter objects
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._invalidate())
 
     def tensor_core_supported(self):
         """Whether the tcgen05 executor covers this network shape (unet_tc.cu build_tc): no LinearAttention, and every
@@ -177,6 +181,7 @@ class TemporalUnet(nn.Module):
         self._handle = None
         self._handle_key = None
         self._keepalive = None
+        self._plist = None
 
     def __del__(self):
         try:
@@ -202,14 +207,18 @@ class TemporalUnet(nn.Module):
     def native(self):
         """mmdk_unet handle for the current weights/device (built lazily, rebuilt after load_state_dict / .to())."""
         lib = _lib.lib()
-        dev = next(self.parameters()).device
+        # the Parameter objects are cached with the handle (walking nn.Module.parameters() costs ~100 us per call, more than
+        # a small-batch forward); _apply / load_state_dict drop the cache, in-place updates are caught by the versions below
+        if getattr(self, "_plist", None) is None:
+            self._plist = list(self.parameters())
+        dev = self._plist[0].device
         if dev.type != "cuda":
             raise _lib.MMDKError("TemporalUnet parameters must live on a CUDA device (no CPU path)")
         # keyed on every parameter's version counter too: load_state_dict through a PARENT module
         # (GaussianDiffusionModel.load_state_dict recurses via _load_from_state_dict and never calls this class's
         # override) and in-place updates (p.data.copy_, optimiser steps) bump `_version`, so stale packed weights on
         # the device can never be used silently
-        key = (dev, self._time_table_steps, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        key = (dev, self._time_table_steps, tuple([(p.data_ptr(), p._version) for p in self._plist]))
         if self._handle is not None and self._handle_key == key:
             return self._handle
         self._release()
@@ -231,6 +240,7 @@ class TemporalUnet(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.mmdk_unet_create(C.byref(cfg), len(names), c_names, c_ptrs, c_numel, _lib.stream_ptr(), C.byref(out)))
         self._handle, self._handle_key, self._keepalive = out, key, sd
+        self._plist = list(self.parameters())
         return out
 
     # -- forward ------------------------------------------------------------------------------------------------

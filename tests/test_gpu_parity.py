@@ -90,6 +90,28 @@ def test_unet_tensor_core_matches_oracle(pair, dev, B):
         assert e < 5e-5
 
 
+def test_weights_reloaded_through_the_parent_module(dev):
+    """mpd.py:167 pattern AFTER a forward has built the native handle: diffusion_model.load_state_dict(ckpt) must reach the
+    device copy of the weights, as must an in-place parameter update."""
+    o = build_oracle("EnvEmpty2D", T=25)
+    p = build_product(dev, "EnvEmpty2D", T=25, P=o["P"])
+    x = torch.randn(4, 64, 4, generator=torch.Generator().manual_seed(0))
+    t = torch.full((4,), 7, dtype=torch.long)
+    for prec in ("fp32", "f16x3"):
+        p["unet"].forward_t(x.to(dev), 7, precision=prec)                 # handle + executor state exist now
+    P2 = port.make_unet_params(seed=5)
+    missing, unexpected = p["model"].load_state_dict({f"model.{k}": v for k, v in P2.items()}, strict=False)
+    assert not unexpected
+    ref2 = port.unet_forward(P2, x, t)
+    for prec in ("fp32", "f16x3"):
+        assert rel_err(p["unet"].forward_t(x.to(dev), 7, precision=prec), ref2) < 5e-5, prec
+    with torch.no_grad():
+        p["unet"].final_conv[1].bias.add_(0.25)
+    P3 = {k: v.clone() for k, v in P2.items()}
+    P3["final_conv.1.bias"] += 0.25
+    assert rel_err(p["unet"].forward_t(x.to(dev), 7, precision="f16x3"), port.unet_forward(P3, x, t)) < 5e-5
+
+
 def test_unet_linear_attention_fp32(dev):
     """self_attention=True: Residual(PreNorm(LinearAttention)) after every level (layers.py:177-229), fp32 executor."""
     import mmd_b200 as M

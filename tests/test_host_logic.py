@@ -112,3 +112,28 @@ def test_global_pad_paths_equals_oracle():
     starts = [4, 0, 1]
     for a, b in zip(M.global_pad_paths(paths, starts), port.global_pad_paths(paths, starts)):
         assert torch.equal(a, b)
+
+
+def test_parent_load_state_dict_invalidates_the_native_handle():
+    """GaussianDiffusionModel.load_state_dict (mpd.py:167 pattern) recurses through _load_from_state_dict and
+    never calls TemporalUnet.load_state_dict; the packed device weights must still be dropped -- by the post hook for any
+    load (also assign=True, which replaces the Parameter objects), by the version counters for in-place updates."""
+    import unittest.mock as mock
+    import mmd_b200 as M
+    u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    m = M.GaussianDiffusionModel(model=u, variance_schedule="exponential", n_diffusion_steps=25, predict_epsilon=True)
+
+    def fake_release(self):
+        self._handle, self._handle_key, self._plist = None, None, None
+
+    with mock.patch.object(type(u), "_release", fake_release):
+        for kw in ({}, {"assign": True}):
+            u._handle, u._handle_key, u._plist = object(), 1, []
+            m.load_state_dict(m.state_dict(), **kw)
+            assert u._handle is None and u._plist is None, kw
+    # in-place update -> the key the handle is compared with changes
+    plist = list(u.parameters())
+    k0 = tuple((p.data_ptr(), p._version) for p in plist)
+    with torch.no_grad():
+        plist[3].add_(1.0)
+    assert tuple((p.data_ptr(), p._version) for p in plist) != k0
