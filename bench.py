@@ -352,11 +352,12 @@ def run_gpu(args):
             per_guided = (1 if world > 1 else 0) + (1 if ws["peer_hash"] is not None else 0)   # wait_peers, build_peer_hash
         # per reverse step: UNet launches + ddpm_step_kernel (publication fused); once per chain: the first publication
         launches_per_chain = n_steps * (n_unet_launches + 1) + n_guided * per_guided + (1 if lock else 0)
-        traffic = None
+        traffic, traffic_source = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp) and args.config == 4 and fused and world == 1:
             tj = json.load(open(tp))
-            traffic = {"bytes_per_launch": tj["dram_bytes_per_launch"], "source": tj["source"]}
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_source = tj["source"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cb_v, nt, sample, _ = cpu_sample(cfg, R_total)
@@ -374,7 +375,7 @@ def run_gpu(args):
             "gpu_launches": launches_per_chain * args.steps,
             "exchange": {"kind": exchange_kind, "timed_out": exchange_failed},
             "roofline": {"bound": "tensor", "kernel": "TemporalUnet forward (" + args.precision + (": unet_fused_kernel, one persistent tcgen05 launch)" if fused else ")"), "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                          "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                         f"the kernel runs kind::f16 MMAs at the bf16 rate and executes 3x the algorithmic FLOP (FP16 hi/lo split)",
                          "algorithmic_flop_per_launch": B * UNET_FLOP_PER_SAMPLE, "avg_launch_ms": unet_avg_ms,

@@ -192,15 +192,21 @@ class MPD:
         """mpd.py:352-405: unnormalise the chain, classify, pick the best free trajectory, smooth."""
         trajs_iters = self.dataset.unnormalize_trajectories(chain)
         trajs_final = trajs_iters[-1]
-        coll, coll_idxs, free, free_idxs, _ = self.task.get_trajs_collision_and_free(trajs_final, return_indices=True)
+        # ONE classification launch serves the free / colliding split, the per-trajectory cost (path length + smoothness do
+        # not depend on the other trajectories) and the collision intensity (tasks.py:236-311, mpd.py:356-382)
+        free_mask, cost_every, wp = self.task.classify(trajs_final, return_waypoints=True)
+        free_b = free_mask.bool()
+        free_idxs, coll_idxs = torch.argwhere(free_b), torch.argwhere(~free_b)
+        free = trajs_final[free_idxs.squeeze(-1)] if free_idxs.numel() else None
+        coll = trajs_final[coll_idxs.squeeze(-1)] if coll_idxs.numel() else None
         out = PlannerOutput()
         n_all = trajs_final.shape[0]
         n_free = 0 if free is None else free.shape[0]
         out.success_free_trajs = 1 if n_free > 0 else 0              # tasks.py compute_success_free_trajs
         out.fraction_free_trajs = n_free / n_all
-        out.collision_intensity_trajs = float(_collision_intensity(self.task, trajs_final))
+        out.collision_intensity_trajs = float(wp.float().mean())     # tasks.py compute_collision_intensity_trajs
         if free is not None:
-            _, cost_all, _ = self.task.classify(free)  # path length + smoothness (TR/trajectory/metrics.py)
+            cost_all = cost_every[free_idxs.squeeze(-1)]
             idx_best_free = int(torch.argmin(cost_all))
             out.idx_best_traj = free_idxs[idx_best_free]
             out.idx_best_free_traj = idx_best_free
@@ -208,7 +214,7 @@ class MPD:
             out.cost_all = cost_all
             out.cost_smoothness = compute_smoothness(free)
             out.cost_path_length = compute_path_length(free)
-            out.variance_waypoint_trajs_final_free = compute_variance_waypoints(free)
+            out.variance_waypoint_trajs_final_free = compute_variance_waypoints(free) if n_free > 1 else torch.zeros((), device=free.device)
             out.traj_final_free_best = free[idx_best_free]
         out.trajs_iters, out.trajs_final = trajs_iters, trajs_final
         out.trajs_final_coll, out.trajs_final_coll_idxs = coll, coll_idxs
