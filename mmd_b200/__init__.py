@@ -17,5 +17,5 @@ from .planners import (MPD, MPDEnsemble, plan_batch, DiffusionsEnsemble, MultiPo
                        PlanningTaskEnsemble)
 from . import envs  # noqa: F401
 from . import conflicts, smoothing  # noqa: F401
-from .conflicts import get_conflicts, count_conflicts_batched, global_pad_paths  # noqa: F401
+from .conflicts import get_conflicts, count_conflicts_batched, global_pad_paths, soft_constraints_from_paths  # noqa: F401
 from .smoothing import smooth_trajs  # noqa: F401

@@ -122,3 +122,35 @@ def get_conflicts(best_path_l, start_time_l, conflict_types=(PointConflict,), ro
             conflicts.append(PointConflict([a, b], p_l=[dense[a, t_dense], dense[b, t_dense]], q_l=[mid, mid],
                                            t_from=int(t_from), t_to=int(t_to)))
     return conflicts
+
+
+def soft_constraints_from_paths(best_path_l, start_time_l, agent_id, radius=2.4 * 0.05, T_agent=None):
+    """CBS.create_soft_constraints_from_other_agents_paths (cbs.py:468-508) without the per-waypoint Python loop: the best
+    paths of the OTHER agents become one soft MultiPointConstraint for `agent_id` -- entry (q = position of agent j at its
+    waypoint t, range (t_a, t_a + 1), radius) with t_a = t + start_time[j] - start_time[agent_id], kept iff 1 <= t_a <= T_agent
+    -- built with a handful of tensor ops on the device, in the reference's order (agents ascending, then t ascending), so
+    the bucketed arrays the step kernel reads are identical.  best_path_l: per agent [H_j, >= 2] (positions first).
+    Returns [] or [MultiPointConstraint] like the reference."""
+    from .planners import MultiPointConstraint
+    if len(best_path_l) == 0:
+        return []
+    if T_agent is None:   # cbs.py:494-497
+        T_agent = (best_path_l[agent_id].shape[0] - 1) if agent_id < len(best_path_l) else None
+    qs, ts = [], []
+    for j, path in enumerate(best_path_l):
+        if j == agent_id:
+            continue
+        Tj = (path.shape[0] - 1) if T_agent is None else T_agent
+        t_a = torch.arange(path.shape[0], device=path.device) + int(start_time_l[j]) - int(start_time_l[agent_id])
+        keep = (t_a >= 1) & (t_a <= Tj)
+        qs.append(path[keep][:, :2])
+        ts.append(t_a[keep])
+    if not qs:
+        return []
+    q = torch.cat(qs, 0)
+    if q.shape[0] == 0:
+        return []
+    t = torch.cat(ts, 0).to(torch.float32)
+    c = MultiPointConstraint(q_l=q, t_range_l=torch.stack((t, t + 1), -1), radius_l=torch.full((q.shape[0],), float(radius)),
+                             is_soft=True)
+    return [c]

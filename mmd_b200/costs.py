@@ -40,7 +40,11 @@ class CostConstraint(Cost):  # cost_functions.py:275-326
     def __init__(self, robot, n_support_points, q_l, traj_range_l, radius_l, is_soft=False, **kwargs):
         super().__init__(robot, n_support_points, **kwargs)
         dev = (self.tensor_args or {}).get("device", None)
-        self.qs = torch.stack([torch.as_tensor(q, dtype=torch.float32) for q in q_l], dim=0).to(dev)
-        self.traj_ranges = torch.tensor(traj_range_l, dtype=torch.float32, device=dev)
-        self.radii = torch.tensor(radius_l, dtype=torch.float32, device=dev)
+        # tensors pass straight through (device-side constraint construction, conflicts.soft_constraints_from_paths)
+        if torch.is_tensor(q_l):
+            self.qs = q_l.to(torch.float32).reshape(-1, q_l.shape[-1]).to(dev)
+        else:
+            self.qs = torch.stack([torch.as_tensor(q, dtype=torch.float32) for q in q_l], dim=0).to(dev)
+        self.traj_ranges = torch.as_tensor(traj_range_l, dtype=torch.float32).reshape(-1, 2).to(dev)
+        self.radii = torch.as_tensor(radius_l, dtype=torch.float32).reshape(-1).to(dev)
         self.is_soft = is_soft

@@ -88,7 +88,8 @@ struct StepArgs {
   float* raw_out;
   int n_costs_max;
   int peers_in_smem;  // the [n_peers, H, 2] table is staged in shared memory once per launch (it is constant during it)
-  int hash_in_smem;   // the peer hash (cell_start + sorted) is staged in shared memory once per launch
+  int hash_in_smem;   // the sorted peer positions of the hash are staged in shared memory once per launch
+  int cs_in_smem;     // the hash's cell_start table is staged in shared memory (fits long after the positions stop fitting)
   // publication of every group's representative sample at the END of the step (it is the x the next step starts from):
   // fused all-gather over peer memory -- the row goes straight into the peer table of every rank (NVLink stores), then
   // the last group to finish releases this rank's sequence number into every rank's flag array
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
   // lock-step peers: constant for the whole launch -> one coalesced copy into shared memory, 20 x reuse
   float2* s_peers = reinterpret_cast<float2*>(s_xu_all + 2 * (size_t)a.spc * H);
   float4* s_sorted = reinterpret_cast<float4*>(s_peers);                                  // hash staging aliases the
-  unsigned short* s_cs = reinterpret_cast<unsigned short*>(s_sorted + (size_t)H * a.grp.n_peers);   // brute-force staging
+  unsigned short* s_cs = reinterpret_cast<unsigned short*>(s_sorted + (a.hash_in_smem ? (size_t)H * a.grp.n_peers : 0));   // brute-force staging
   // double-buffered table: readers use the half of the current sequence number, the publication at the end of this launch
   // writes the other half
   const size_t peer_half = (a.grp.peers_dev && a.grp.peer_seq_dev) ? (size_t)(*a.grp.peer_seq_dev & 1u) * a.grp.n_peers * H : 0;
@@ -196,10 +197,12 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
     for (int i = tid; i < a.grp.n_peers * H; i += blockDim.x) s_peers[i] = __ldg(gp + i);
     __syncthreads();
   }
-  if (a.hash_in_smem) {
+  if (a.hash_in_smem || a.cs_in_smem) {
     const int G2 = a.grp.peer_grid * a.grp.peer_grid + 1;
-    const float4* gs = reinterpret_cast<const float4*>(a.grp.peer_sorted_dev);
-    for (int i = tid; i < H * a.grp.n_peers; i += blockDim.x) s_sorted[i] = __ldg(gs + i);
+    if (a.hash_in_smem) {
+      const float4* gs = reinterpret_cast<const float4*>(a.grp.peer_sorted_dev);
+      for (int i = tid; i < H * a.grp.n_peers; i += blockDim.x) s_sorted[i] = __ldg(gs + i);
+    }
     for (int i = tid; i < H * G2; i += blockDim.x) s_cs[i] = a.grp.peer_cell_start_dev[i];
     __syncthreads();
   }
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(512, 2) ddpm_step_kernel(const StepArgs a) {
       const float r2_far = r * r * 1.0001f;
       if (a.grp.peer_cell_start_dev) {
         const int G = a.grp.peer_grid;
-        const unsigned short* cs = (a.hash_in_smem ? s_cs : a.grp.peer_cell_start_dev) + (size_t)h * (G * G + 1);
+        const unsigned short* cs = (a.cs_in_smem ? s_cs : a.grp.peer_cell_start_dev) + (size_t)h * (G * G + 1);
         const float4* sp = (a.hash_in_smem ? s_sorted : reinterpret_cast<const float4*>(a.grp.peer_sorted_dev)) + (size_t)h * a.grp.n_peers;
         int cx, cy;
         peer_cell(a.grp.peer_grid_lo, a.grp.peer_grid_inv_cell, G, xu[0], xu[1], cx, cy);
@@ -458,9 +461,8 @@ static int launch_step(const StepArgs& args, bool taps, cudaStream_t stream) {
   const int threads = args.H * args.spc;
   size_t smem = 2 * sizeof(float4) * (size_t)args.H * args.spc;
   if (args.peers_in_smem) smem += sizeof(float2) * (size_t)args.grp.n_peers * args.H;
-  if (args.hash_in_smem)
-    smem += sizeof(float4) * (size_t)args.grp.n_peers * args.H +
-            sizeof(unsigned short) * (size_t)args.H * (args.grp.peer_grid * args.grp.peer_grid + 1);
+  if (args.hash_in_smem) smem += sizeof(float4) * (size_t)args.grp.n_peers * args.H;
+  if (args.cs_in_smem) smem += sizeof(unsigned short) * (size_t)args.H * (args.grp.peer_grid * args.grp.peer_grid + 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(args.grp.n_groups * args.cpg));
   cfg.blockDim = dim3((unsigned)threads);
@@ -522,10 +524,14 @@ static int plan_step(StepArgs& a) {
   a.cpg = cpg;
   a.peers_in_smem = (a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev == nullptr &&
                      2 * sizeof(float4) * (size_t)H * spc + sizeof(float2) * (size_t)a.grp.n_peers * H <= 100 * 1024) ? 1 : 0;
-  // two CTAs per SM: stage the hash only while both fit comfortably (<= ~100 KB each)
-  a.hash_in_smem = (a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev != nullptr &&
-                    2 * sizeof(float4) * (size_t)H * spc + sizeof(float4) * (size_t)a.grp.n_peers * H +
-                    sizeof(unsigned short) * (size_t)H * (a.grp.peer_grid * a.grp.peer_grid + 1) <= 100 * 1024) ? 1 : 0;
+  // two CTAs per SM: stage the hash only while both fit comfortably (<= ~100 KB each); the cell_start table alone (46 KB at
+  // the default radius) still fits when the sorted positions (16 B x peers x H) no longer do -- then the 3x3-cell walk reads
+  // its offsets from shared memory and only the few candidate positions from L2
+  const size_t cs_bytes = sizeof(unsigned short) * (size_t)H * (a.grp.peer_grid * a.grp.peer_grid + 1);
+  const size_t xu_bytes = 2 * sizeof(float4) * (size_t)H * spc;
+  const bool hashed = a.grp.peers_dev != nullptr && a.grp.peer_cell_start_dev != nullptr;
+  a.cs_in_smem = (hashed && xu_bytes + cs_bytes <= 100 * 1024) ? 1 : 0;
+  a.hash_in_smem = (a.cs_in_smem && xu_bytes + cs_bytes + sizeof(float4) * (size_t)a.grp.n_peers * H <= 100 * 1024) ? 1 : 0;
   if (a.grp.peer_cell_start_dev && (a.grp.peer_grid < 1 || a.grp.peer_grid > MMDK_PEER_GRID_MAX || !a.grp.peer_sorted_dev))
     return fail(MMDK_EINVAL, "peer hash: bad grid size or missing sorted table");
   return MMDK_OK;

@@ -832,6 +832,29 @@ def get_conflicts(best_path_l, start_time_l, want_vertex=False, want_edge=False,
     return out
 
 
+def create_soft_constraints_from_other_agents_paths(best_path_l, start_time_l, agent_id, radius=2.4 * ROBOT_RADIUS):
+    """cbs.py:468-508, loops kept as in the reference.  Returns (q [n, 2], t_range [n, 2], radii [n]) or None."""
+    if len(best_path_l) == 0:
+        return None
+    q_l, t_range_l, radius_l = [], [], []
+    for other in range(len(best_path_l)):
+        if other != agent_id:
+            path = best_path_l[other]
+            for t_other in range(0, len(path), 1):
+                t_agent = t_other + start_time_l[other] - start_time_l[agent_id]
+                if agent_id >= len(best_path_l):
+                    T_agent = len(path) - 1
+                else:
+                    T_agent = len(best_path_l[agent_id]) - 1
+                if 1 <= t_agent <= T_agent:
+                    q_l.append(path[t_other][:2])
+                    t_range_l.append((t_agent, t_agent + 1))
+                    radius_l.append(radius)
+    if not q_l:
+        return None
+    return torch.stack(q_l), torch.tensor(t_range_l, dtype=torch.float32), torch.tensor(radius_l)
+
+
 def smooth_trajs(trajs, window_size=10, poly_order=2):  # trajectory_utils.py:31-38 (scipy on the host, as the reference)
     from scipy.signal import savgol_filter
     return torch.tensor(savgol_filter(trajs.cpu().numpy(), window_size, poly_order, axis=1))

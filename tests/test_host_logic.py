@@ -137,3 +137,29 @@ def test_parent_load_state_dict_invalidates_the_native_handle():
     with torch.no_grad():
         plist[3].add_(1.0)
     assert tuple((p.data_ptr(), p._version) for p in plist) != k0
+
+
+def test_soft_constraints_from_paths_equals_the_reference_loops():
+    """f4: vectorised construction == cbs.py:468-508 restated with its loops, ragged start times included, and the
+    resulting CostConstraint buckets identically."""
+    import mmd_b200 as M
+    from mmd_b200.conflicts import soft_constraints_from_paths
+    from mmd_b200.guides import ConstraintSet
+    g = torch.Generator().manual_seed(3)
+    paths = [torch.rand(64, 4, generator=g) * 2 - 1 for _ in range(5)]
+    starts = [0, 3, 0, 7, 1]
+    for agent in range(5):
+        ref = port.create_soft_constraints_from_other_agents_paths(paths, starts, agent)
+        out = soft_constraints_from_paths(paths, starts, agent)
+        assert len(out) == 1 and out[0].is_soft
+        q, rng, rad = ref
+        assert torch.equal(out[0].get_q_l(), q) and torch.equal(torch.as_tensor(out[0].get_t_range_l()), rng)
+        assert torch.allclose(torch.as_tensor(out[0].radius_l), rad)
+        ta = {"device": torch.device("cpu"), "dtype": torch.float32}
+        robot = M.RobotPlanarDisk(tensor_args=ta)
+        c_vec = M.CostConstraint(robot, 64, q_l=out[0].get_q_l(), traj_range_l=out[0].get_t_range_l(), radius_l=out[0].radius_l,
+                                 is_soft=True, tensor_args=ta)
+        c_ref = M.CostConstraint(robot, 64, q_l=list(q), traj_range_l=rng.tolist(), radius_l=rad.tolist(), is_soft=True, tensor_args=ta)
+        a, b = ConstraintSet([c_vec], [2e-2], 64, torch.device("cpu")), ConstraintSet([c_ref], [2e-2], 64, torch.device("cpu"))
+        assert torch.equal(a.bucket_ptr, b.bucket_ptr) and torch.equal(a.cons, b.cons)
+    assert soft_constraints_from_paths([], [], 0) == []

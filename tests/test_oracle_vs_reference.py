@@ -186,3 +186,26 @@ def test_reference_cost_objects_lower_like_ours(env_name):
     cc_own = M.CostConstraint(robot, 64, q_l=list(qs), traj_range_l=rng.tolist(), radius_l=rad.tolist(), is_soft=True, tensor_args=ta)
     s_ref, s_own = ConstraintSet([cc_ref], [2e-2], 64, cpu), ConstraintSet([cc_own], [2e-2], 64, cpu)
     assert torch.equal(s_ref.bucket_ptr, s_own.bucket_ptr) and torch.equal(s_ref.cons, s_own.cons)
+
+
+def test_soft_constraints_from_other_agents_matches_reference(ref):
+    """oracle.port.create_soft_constraints_from_other_agents_paths == the reference's CBS method (cbs.py:468-508), called
+    unbound on a minimal stand-in for the CBS object / SearchState."""
+    import types
+    from oracle import ref_shim
+    ref_shim.install()
+    from mmd.planners.multi_agent.cbs import CBS
+    g = torch.Generator().manual_seed(3)
+    K = 3
+    path_bl = [torch.rand(K, 64, 4, generator=g) * 2 - 1 for _ in range(4)]
+    best = [1, 0, 2, 1]
+    starts = [0, 4, 0, 2]
+    fake = types.SimpleNamespace(reference_robot=ref["robot"], start_time_l=starts)
+    state = types.SimpleNamespace(path_bl=path_bl, ix_best_path_in_batch_l=best)
+    for agent in range(4):
+        out = CBS.create_soft_constraints_from_other_agents_paths(fake, state, agent)
+        assert len(out) == 1
+        q, rng, rad = port.create_soft_constraints_from_other_agents_paths([path_bl[j][best[j]] for j in range(4)], starts, agent)
+        assert torch.equal(torch.stack(out[0].get_q_l()), q)
+        assert torch.equal(torch.tensor(out[0].get_t_range_l(), dtype=torch.float32), rng)
+        assert torch.allclose(torch.tensor(out[0].radius_l), rad) and out[0].is_soft
