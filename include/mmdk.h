@@ -77,6 +77,8 @@ void mmdk_unet_destroy(mmdk_unet* net);
 
 /* eps = TemporalUnet.forward(x, t, context=None) for an integer timestep t shared by the batch
  * (temporal_unet.py:121-174; make_timesteps, diffusion_model_base.py:27-29).  x_dev, eps_dev: [B, H, D]. */
+/* A handle owns its executor state (activation workspace per batch size, the per-forward patch of the layer program): use
+ * a handle from ONE host thread and ONE stream at a time; concurrent streams need one handle each (the weights are small). */
 int mmdk_unet_forward(const mmdk_unet* net, int mode, const float* x_dev, int B, int t, float* eps_dev, void* stream);
 
 /* Debug/parity tap: copies the precomputed cond table row of timestep t ([n_cond] floats) to out_dev. */

@@ -182,9 +182,19 @@ def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_step
         assert chain_steps.is_contiguous() and chain_steps.shape[0] >= n and tuple(chain_steps.shape[1:]) == (B, H, D)
     unet = model.model
     unet.ensure_time_table(max(t for t, _ in steps) + 1)
-    mode = _lib.UNET_MODES[unet.resolve_precision(model.unet_precision)]
-    _lib.check(lib.mmdk_run_chain(unet.native(), mode, C.byref(env), C.byref(grp), C.byref(desc), H, _lib.ptr(x), _lib.ptr(eps),
-                                  _lib.ptr(noise_steps), _lib.ptr(chain_steps), int(bool(use_graph)), _lib.stream_ptr()))
+    def issue():
+        mode = _lib.UNET_MODES[unet.resolve_precision(model.unet_precision)]
+        _lib.check(lib.mmdk_run_chain(unet.native(), mode, C.byref(env), C.byref(grp), C.byref(desc), H, _lib.ptr(x), _lib.ptr(eps),
+                                      _lib.ptr(noise_steps), _lib.ptr(chain_steps), int(bool(use_graph)), _lib.stream_ptr()))
+    try:
+        issue()
+    except ValueError:
+        # unet_precision='auto' on a shape the tensor-core builder rejects: the exact native executor instead (the builder
+        # fails before the first launch of the chain, so x is untouched)
+        if (model.unet_precision or unet.unet_precision) != "auto" or unet.resolve_precision(model.unet_precision) == "fp32":
+            raise
+        unet._tc_rejected = True
+        issue()
     return keep
 
 

@@ -167,6 +167,8 @@ class TemporalUnet(nn.Module):
         """'auto' (default): the tensor-core executor ("f16x3": FP16 hi/lo split, ~3e-6 relative on eps) when the shape is
         supported, else the exact fp32 CUDA-core executor.  Both are native sm_100a kernels."""
         p = precision or self.unet_precision
+        if p == "auto" and getattr(self, "_tc_rejected", False):
+            return "fp32"   # the native builder refused this shape once (ValueError): exact executor from then on
         if p == "auto":
             p = "f16x3" if self.tensor_core_supported() else "fp32"
         return p
@@ -262,6 +264,14 @@ class TemporalUnet(nn.Module):
         h = self.native()
         if out is None:
             out = torch.empty_like(x)
-        mode = _lib.UNET_MODES[self.resolve_precision(precision)]
-        _lib.check(lib.mmdk_unet_forward(h, mode, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
+        chosen = self.resolve_precision(precision)
+        try:
+            _lib.check(lib.mmdk_unet_forward(h, _lib.UNET_MODES[chosen], _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
+        except ValueError:
+            # 'auto' may only ever fall back to the exact NATIVE executor (never to a CPU / torch path), and only when the
+            # tensor-core builder rejects the network shape; an explicit precision request fails loudly
+            if (precision or self.unet_precision) != "auto" or chosen == "fp32":
+                raise
+            self._tc_rejected = True
+            _lib.check(lib.mmdk_unet_forward(h, _lib.UNET_FP32, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
         return out
