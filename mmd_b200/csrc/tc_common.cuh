@@ -32,7 +32,7 @@ struct ChunkDesc {
   int k16;           // 16-channel K steps in this chunk (1 or 2)
 };
 
-enum TcKind : int { TC_CONVBLOCK = 0, TC_DOWN = 1, TC_UP = 2, TC_FINAL = 3 };
+enum TcKind : int { TC_CONVBLOCK = 0, TC_DOWN = 1, TC_UP = 2, TC_FINAL = 3, TC_ATTN_QKV = 4, TC_ATTN_CORE = 5, TC_ATTN_OUT = 6 };
 
 struct TcOpParams {
   int kind, L, P, n_mt, rows, N, cout, B, n_tiles;
@@ -228,16 +228,35 @@ __device__ __forceinline__ void add8(const uint4& hi, const uint4& lo, float* y)
 // ------------------------------------------------------------------------------------------------------------------
 // one weight chunk: W [cin][ktaps][cout] fp32 -> [plane][CK/8][N][8] fp16 (hi | lo)
 static __global__ void pack_wchunk_kernel(const float* __restrict__ W, int cin, int ktaps, int cout, int tap, int ci0, int CK,
-                                   int N, __half* __restrict__ dst) {
+                                   int N, __half* __restrict__ dst, int n0 = 0, const float* __restrict__ scale = nullptr) {
+  // n0: first output channel of this N-column slice (1x1 convs wider than one MMA N are cut into slices); scale: optional
+  // per-input-channel factor folded into the weights (LayerNorm gain of the attention block's PreNorm)
   const int n_el = CK * N;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_el; idx += gridDim.x * blockDim.x) {
     const int e = idx & 7, n = (idx >> 3) % N, kp = idx / (8 * N);
     const int ci = ci0 + kp * 8 + e;
-    float w = (ci < cin && n < cout) ? W[((size_t)ci * ktaps + tap) * cout + n] : 0.f;
+    float w = (ci < cin && n0 + n < cout) ? W[((size_t)ci * ktaps + tap) * cout + n0 + n] : 0.f;
+    if (scale != nullptr && ci < cin) w *= scale[ci];
     __half h = __float2half_rn(w);
     dst[idx] = h;
     dst[n_el + idx] = __float2half_rn(w - __half2float(h));
   }
+}
+
+// LinearAttention PreNorm folding (layers.py:186-229): qkv = W^T LN(x) = rstd (x^T G - mean s) + u with G[c][n] = g[c] W[c][n],
+// s[n] = sum_c G[c][n], u[n] = sum_c b[c] W[c][n].  W: [C][n_out] fp32 (packed 1x1 conv), g / b: [C].
+static __global__ void attn_fold_kernel(const float* __restrict__ W, const float* __restrict__ g, const float* __restrict__ b, int C,
+                                        int n_out, float* __restrict__ s_out, float* __restrict__ u_out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_out) return;
+  float s = 0.f, u = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float w = W[(size_t)c * n_out + n];
+    s = fmaf(g[c], w, s);
+    u = fmaf(b[c], w, u);
+  }
+  s_out[n] = s;
+  u_out[n] = u;
 }
 
 // network input x [B][L][D] fp32 -> level-0 image with C = 16 (channels D..15 stay zero)

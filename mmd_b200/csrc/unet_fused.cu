@@ -77,6 +77,16 @@ struct FOp {
   // in-place activation hand-over inside shared memory: this op's epilogue writes its output image straight into the tile's
   // (now free) input buffer, where the next op of the same tile reads it as its A operand -- no L2 round trip on the tile's
   // critical path; the global image is written only when a later op needs it (identity residual, skip concat, debug taps)
+  // LinearAttention (layers.py:210-229) on this executor: TC_ATTN_QKV ops (one N-slice of the to_qkv 1x1 conv each; the PreNorm
+  // LayerNorm is folded into the weights and undone per row in the epilogue) write fp32 q / k / v rows into per-slot scratch,
+  // TC_ATTN_CORE (no MMA) does softmax over positions, the 32x32 context per (sample, head) and context^T q, TC_ATTN_OUT is the
+  // to_out 1x1 conv + bias + residual.
+  float* aux0;      // QKV: destination scratch of this slice (already offset by the slice's first column); CORE: q
+  float* aux1;      // CORE: k
+  float* aux2;      // CORE: v
+  int aux_ld;       // floats per scratch row (128) ; QKV: unused
+  int src_C;        // channels of the (single) input image: QKV needs them for the LayerNorm statistics
+  int q_base;       // ATTN_OUT over a half-height `out` image (4 m-tile levels): first tile row this op covers (0 / 256)
   int in_smem;      // input already in the parity's buffer (placed by the previous op's epilogue): the producer copies nothing
   int out_smem;     // write the output image into the parity's buffer
   int out_global;   // write the output image to global memory
@@ -90,7 +100,7 @@ struct __align__(16) FChunk {
   uint32_t w_off;    // byte offset of the packed weights relative to the op's wchunks
   uint32_t meta;     // acc | first << 1 | k16 << 2
 };
-constexpr int F_MAX_OPS = 40, F_MAX_CHUNKS = 448;
+constexpr int F_MAX_OPS = 64, F_MAX_CHUNKS = 512;
 
 // The op and chunk tables live in the kernel PARAMETER bank (16 KB of the 32 KB CUDA 12 allows): indexed by warp-uniform
 // loop counters they are read with uniform constant loads, so the MMA issuer's descriptor arithmetic stays in uniform
@@ -110,6 +120,8 @@ struct FParams {
   FOp ops[F_MAX_OPS];
   FChunk chunks[F_MAX_CHUNKS];
 };
+
+static_assert(sizeof(FParams) <= 32764, "kernel parameter bank (CUDA 12: 32,764 bytes)");
 
 // barrier slots
 constexpr int B_IN_FULL = 0, B_IN_EMPTY = 2, B_ACC_FULL = 4, B_ACC_EMPTY = 6, B_OUT_DONE = 8, B_W_FULL = 10,
@@ -149,6 +161,8 @@ struct EpiCtx {
   float2* stat;      // [ST * 8] (-mean * rstd, rstd) of this item
   uint32_t tmem;     // TMEM address of this item's accumulators (lane 0, first column)
   uint8_t* sbuf;     // the parity's input buffer (shared memory), target of the in-place output
+  const uint8_t* inbuf;   // shared-memory buffer holding THIS item's input image(s)
+  int slot;          // (CTA, parity) index of the per-slot scratch
   int tile, img, B, st;   // st = samples per tile of this launch
   long long* dbg;    // this item's stamp row (CTA 0, thread 0 only) or nullptr
 };
@@ -460,13 +474,15 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
     for (int region = 0; region < n_regions; ++region) {
 #pragma unroll 1
       for (int i = 0; i < NMT; ++i) {
-        const int q = 128 * i + c.row;
+        const int q = ((op->kind == TC_ATTN_OUT) ? op->q_base : 0) + 128 * i + c.row;
         const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
         bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
         int ro;
         if (op->kind == TC_DOWN) {   // stride-2 conv evaluated at every position; keep the even ones
           ok = ok && ((pi & 1) == 0);
           ro = 2 + si * Po + (pi >> 1);
+        } else if (op->kind == TC_ATTN_OUT) {   // to_out 1x1 conv at the same resolution (+ bias + residual x below)
+          ro = 2 + q;
         } else {                      // transposed conv: region 0 -> output 2p, region 1 -> 2p + 1
           ro = 2 + si * Po + 2 * pi + region;
         }
@@ -480,6 +496,11 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
           if (ok) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] += c.p_bias[cbase + e];
+            if (op->kind == TC_ATTN_OUT && op->res_id != nullptr) {   // Residual(...): + x
+              const uint8_t* rp = op->res_id + (size_t)c.img * op->res_id_tile_bytes + ((size_t)(cbase / 8) * op->res_id_rows + 2 + q) * 16;
+              const uint4 rh = ld_cg_u4(rp), rl = ld_cg_u4(rp + (size_t)(op->res_id_C / 8) * op->res_id_rows * 16);
+              add8(rh, rl, y);
+            }
             uint4 hi, lo;
             split8(y, hi, lo);
             uint8_t* ob = obase + (size_t)(cbase / 8) * op->out_rows * 16;
@@ -493,6 +514,119 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(bar_acc_empty);
+}
+
+// ---- LinearAttention epilogues ------------------------------------------------------------------------------------------
+// TC_ATTN_QKV: acc[row][n] = sum_c x[row][c] g[c] W[c][n] (raw x, gain folded into the weights).  Per row: LayerNorm statistics
+// of x over the C channels from the input image in shared memory, then y = rstd (acc - mean s[n]) + u[n] (s = p_gamma,
+// u = p_bias), stored as fp32 into the slot's scratch.
+__device__ __forceinline__ void epi_attn_qkv(const FOp* __restrict__ op, const EpiCtx& c, uint32_t bar_acc_empty) {
+  const int N = op->N, NMT = op->n_mt, L = op->L, Pp = op->P, C = op->src_C;
+  const int NH = N / 4, c0 = c.cb * NH;
+  const uint32_t lane_base = c.tmem + ((uint32_t)(c.q4 * 32) << 16);
+  const uint32_t pinv = (65536u + (uint32_t)Pp - 1u) / (uint32_t)Pp;
+  const int rows = (int)(op->src_lbo[0] >> 4);
+  const uint8_t* img = c.inbuf + op->src_smem_off[0];
+  const size_t plane = op->src_plane[0];
+  const int ppq = C / 32;                      // 8-channel panels per column-block thread (the 4 threads of a row split the channels)
+  // partial (sum, sum of squares) of this thread's channels, every m-tile
+  for (int i = 0; i < NMT; ++i) {
+    const int q = 128 * i + c.row;
+    float sm = 0.f, sq = 0.f;
+    for (int pp = 0; pp < ppq; ++pp) {
+      const uint8_t* pr = img + ((size_t)(c.cb * ppq + pp) * rows + 2 + q) * 16;
+      const uint4 hi = *reinterpret_cast<const uint4*>(pr), lo = *reinterpret_cast<const uint4*>(pr + plane);
+      const __half2* h = reinterpret_cast<const __half2*>(&hi);
+      const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(h[e]), b = __half22float2(l[e]);
+        const float x0 = a.x + b.x, x1 = a.y + b.y;
+        sm += x0 + x1;
+        sq = fmaf(x0, x0, fmaf(x1, x1, sq));
+      }
+    }
+    c.part[c.cb * F_PART_ROWS + q] = make_float2(sm, sq);
+  }
+  epi_bar16();
+  const float inv_c = 1.f / (float)C;
+  for (int i = 0; i < NMT; ++i) {
+    const int q = 128 * i + c.row;
+    const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
+    const bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 e = c.part[j * F_PART_ROWS + q]; sm += e.x; sq += e.y; }
+    const float mean = sm * inv_c;
+    const float rstd = rsqrtf(fmaxf(sq * inv_c - mean * mean, 0.f) + 1e-5f);
+    float* dst = op->aux0 + ((size_t)c.slot * (128 * NMT) + q) * op->aux_ld + c0;
+    for (int pc = 0; pc < NH / 8; ++pc) {
+      float y[8];
+      tmem_ld8(lane_base + i * N + c0 + pc * 8, y);
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = fmaf(rstd, y[e] - mean * c.p_gamma[c0 + pc * 8 + e], c.p_bias[c0 + pc * 8 + e]);
+        *reinterpret_cast<float4*>(dst + pc * 8) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(dst + pc * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (c.lane == 0) mbar_arrive(bar_acc_empty);
+}
+
+// TC_ATTN_CORE: per (sample, head) one warp, lane = channel of the head.  k is soft-maxed over the L positions, context^T[e][d] =
+// sum_n v[n][e] p[n][d] lives in registers (lane e holds row e), out[n][e] = scale sum_d context[d][e] q[n][d]; `out` is stored
+// as the hi/lo tile image the to_out GEMM reads.  heads = 4, dim_head = 32 (layers.py:211).
+__device__ __forceinline__ void epi_attn_core(const FOp* __restrict__ op, const EpiCtx& c, uint32_t bar_acc_empty) {
+  if (c.lane == 0) mbar_arrive(bar_acc_empty);   // no accumulators in this op
+  epi_bar16();                                   // every thread's q / k / v stores of the previous items are visible
+  const int L = op->L, Pp = op->P, ld = op->aux_ld;
+  const int rows_q = 128 * op->n_mt;
+  const float* qb = op->aux0 + (size_t)c.slot * rows_q * ld;
+  const float* kb = op->aux1 + (size_t)c.slot * rows_q * ld;
+  const float* vb = op->aux2 + (size_t)c.slot * rows_q * ld;
+  const size_t oplane = (size_t)(op->out_C / 8) * op->out_rows * 16;
+  uint8_t* oimg = op->out + (size_t)c.img * op->out_tile_bytes;
+  uint8_t* oimg2 = op->out2 ? op->out2 + (size_t)c.img * op->out2_tile_bytes : nullptr;   // rows >= 256 (half-height images)
+  const int lane = c.lane;
+  for (int pair = c.warp; pair < c.st * 4; pair += FE_WARPS) {
+    const int s = pair >> 2, h = pair & 3;
+    if (c.tile * c.st + s >= c.B) continue;
+    const int col = h * 32 + lane;
+    const int q0 = s * Pp;
+    // softmax statistics of k[:, col] over the positions
+    float mx = -INFINITY;
+    for (int n = 0; n < L; ++n) mx = fmaxf(mx, kb[(size_t)(q0 + n) * ld + col]);
+    float sum = 0.f;
+    for (int n = 0; n < L; ++n) sum += expf(kb[(size_t)(q0 + n) * ld + col] - mx);
+    const float inv = 1.f / sum;
+    float ctx[32];                               // lane e: context[d][e] for d = 0 .. 31
+#pragma unroll
+    for (int d = 0; d < 32; ++d) ctx[d] = 0.f;
+    for (int n = 0; n < L; ++n) {
+      const float pk = expf(kb[(size_t)(q0 + n) * ld + col] - mx) * inv;   // lane d: softmax(k)[n][d]
+      const float ve = vb[(size_t)(q0 + n) * ld + col];                    // lane e: v[n][e]
+#pragma unroll
+      for (int d = 0; d < 32; ++d) ctx[d] = fmaf(ve, __shfl_sync(0xffffffffu, pk, d), ctx[d]);
+    }
+    for (int n = 0; n < L; ++n) {
+      const float qd = qb[(size_t)(q0 + n) * ld + col] * 0.17677669529663687f;   // q * dim_head^-0.5
+      float o = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) o = fmaf(ctx[d], __shfl_sync(0xffffffffu, qd, d), o);
+      const __half oh = __float2half_rn(o);
+      const __half ol = __float2half_rn(o - __half2float(oh));
+      const int qr = q0 + n;
+      uint8_t* ob = (oimg2 != nullptr && qr >= 256) ? oimg2 + ((size_t)(col >> 3) * op->out_rows + 2 + qr - 256) * 16
+                                                    : oimg + ((size_t)(col >> 3) * op->out_rows + 2 + qr) * 16;
+      __half* dsth = reinterpret_cast<__half*>(ob) + (col & 7);
+      *dsth = oh;
+      *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(dsth) + oplane) = ol;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_constant__ FParams P) {
@@ -728,6 +862,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
       // in-place hand-over target = the buffer the NEXT op of this tile will use: items alternate buffers, so it is this
       // item's own (free) buffer while the round has two tiles, and the other buffer in a single-tile round
       c.sbuf = smem + (size_t)((2 * r_ + 1 < n_my) ? p : (p ^ 1)) * P.buf_bytes;
+      c.inbuf = smem + (op->big ? 0u : (uint32_t)p * P.buf_bytes);
+      c.slot = (int)blockIdx.x * 2 + par;
       c.dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg + (size_t)k * 16 : nullptr;
       if (tid == 0) FSTAMP(k, 7);
       // per-channel parameters of this item: staged by the producer warp into bank p
@@ -745,6 +881,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
           case FV_1_32: epi_convblock<1, 32>(op, c, bae); break;
           default: epi_convblock<1, 64>(op, c, bae); break;
         }
+      } else if (op->kind == TC_ATTN_QKV) {
+        epi_attn_qkv(op, c, bae);
+      } else if (op->kind == TC_ATTN_CORE) {
+        epi_attn_core(op, c, bae);
       } else {
         epi_plain(op, c, bae, P.eps);
       }
@@ -804,7 +944,6 @@ void unet_fused_release(UnetImpl* net) {
 
 static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStream_t stream, FusedState** out) {
   const auto& cfg = net->cfg;
-  if (cfg.self_attention) return fail(MMDK_EINVAL, "tensor-core executor: LinearAttention not supported");
   if (cfg.state_dim > 8) return fail(MMDK_EINVAL, "tensor-core executor: state_dim > 8 not supported");
   int dev = 0, n_sm = 0, max_smem = 0;
   MMDK_CUDA(cudaGetDevice(&dev));
@@ -826,13 +965,14 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   st->keep_all = keep_all;
   const int n_img = by_slot ? 2 * st->grid : st->n_tiles;   // entries of every intermediate image
   const int n_ops = (int)net->ops.size();
+  st->images.reserve(n_ops + 1 + 16);    // [n_ops + 1 ..]: internal images of the attention blocks (references stay valid)
   st->images.resize(n_ops + 1);
   st->images_r.resize(n_ops);
-  st->ops.resize(n_ops);
+  st->ops.reserve(F_MAX_OPS + 8);        // FOp list: one per layer op, several per LinearAttention block
   auto fail_free = [&](const std::string& m) { fused_free(st); return fail(MMDK_EINVAL, m); };
 
-  auto make_image = [&](TcImage& im, int C, int L, int entries) -> int {
-    im.C = C; im.L = L; im.rows = level_rows(L, st->st);
+  auto make_image = [&](TcImage& im, int C, int L, int entries, int rows_override = 0) -> int {
+    im.C = C; im.L = L; im.rows = rows_override ? rows_override : level_rows(L, st->st);
     im.tile_bytes = (uint32_t)C * im.rows * 4;
     const size_t bytes = (size_t)im.tile_bytes * entries;
     if (cudaMalloc(&im.dev, bytes) != cudaSuccess) return MMDK_ENOMEM;
@@ -844,16 +984,137 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   if (make_image(st->images[0], 16, cfg.horizon, st->n_tiles) != MMDK_OK) return fail_free("out of memory (input image)");
 
   std::vector<FChunk> all_chunks;
-  struct WSrc { const float* W; int cin, ktaps, tap, ci0, CK, cout, N; uint32_t dst_off; };
+  struct WSrc { const float* W; int cin, ktaps, tap, ci0, CK, cout, N; uint32_t dst_off; int n0; const float* scale; };
   std::vector<WSrc> wsrc;
   uint32_t w_total = 0;
-  std::vector<uint32_t> op_w_off(n_ops, 0);
+  std::vector<uint32_t> op_w_off;     // per FOp
   uint32_t max_in = 0;
-  std::vector<uint32_t> in_bytes(n_ops, 0);
+  std::vector<uint32_t> in_bytes;     // per FOp
+  struct HChunk { uint32_t a_off, w_off, w_bytes; int d, acc, first, k16, slot; };
+  std::string ferr;
+  // chunk list of one FOp -> packed descriptors; bookkeeping shared by layer ops and attention ops
+  auto finalize_op = [&](FOp& p, const std::vector<HChunk>& chunks, uint32_t off) -> bool {
+    p.in_bytes = off;
+    in_bytes.push_back(off);
+    max_in = std::max(max_in, off);
+    p.chunk_base = (int)all_chunks.size();
+    p.n_chunks = (int)chunks.size();
+    op_w_off.push_back(chunks.empty() ? w_total : chunks[0].w_off);   // chunk weight offsets are relative to the op's base
+    for (const auto& cd : chunks) {
+      FChunk fc{};
+      const uint32_t lbo = p.src_lbo[cd.slot], plane = p.src_plane[cd.slot];
+      fc.a_w = (((cd.a_off + (uint32_t)((2 + cd.d) * 16)) >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+      if (((2 * lbo) >> 4) > 0xFFFFu || (plane >> 4) > 0xFFFFu) { ferr = "tensor-core executor: image too large for the packed chunk descriptor"; return false; }
+      fc.a_ks_pl = ((2 * lbo) >> 4) | ((plane >> 4) << 16);
+      fc.w_off = cd.w_off - op_w_off.back();
+      fc.meta = (uint32_t)cd.acc | ((uint32_t)cd.first << 1) | ((uint32_t)cd.k16 << 2);
+      all_chunks.push_back(fc);
+    }
+    return true;
+  };
+  // one 1x1-conv GEMM over a single input image (attention projections): source slot 0, tap 0, region 0
+  auto gemm_1x1 = [&](FOp& p, std::vector<HChunk>& chunks, uint32_t& off, const TcImage& im, const float* W, int cin, int cout_total,
+                      int n0, const float* scale) {
+    p.n_src = 1;
+    p.src[0] = im.dev; p.src_by_tile[0] = 0; p.src_tile_bytes[0] = im.tile_bytes; p.src_smem_off[0] = 0;
+    p.src_lbo[0] = (uint32_t)im.rows * 16;
+    p.src_plane[0] = (uint32_t)(im.C / 8) * im.rows * 16;
+    off = (im.tile_bytes + 127) & ~127u;
+    for (int c0 = 0; c0 < im.C; c0 += 32) {
+      const int CK = std::min(32, im.C - c0);
+      HChunk cd{};
+      cd.a_off = (uint32_t)(c0 / 8) * im.rows * 16;
+      cd.slot = 0;
+      cd.w_bytes = (uint32_t)CK * p.N * 4;
+      cd.w_off = w_total;
+      wsrc.push_back({W, cin, 1, 0, c0, CK, cout_total, p.N, w_total, n0, scale});
+      w_total += cd.w_bytes;
+      cd.d = 0; cd.acc = 0; cd.first = (c0 == 0) ? 1 : 0; cd.k16 = CK / 16;
+      chunks.push_back(cd);
+    }
+  };
 
   for (int j = 0; j < n_ops; ++j) {
     const Op& op = net->ops[j];
-    FOp& p = st->ops[j];
+    if (op.type == OP_ATTN) {
+      // ---- Residual(PreNorm(LinearAttention)) (layers.py:177-229) -> QKV slices, core, to_out ------------------------------
+      const int C = op.cin, Lx = op.lin;
+      const int rows = level_rows(Lx, st->st), n_mt = (rows - 4) / 128;
+      if ((C != 32 && C != 64 && C != 128) || (n_mt != 1 && n_mt != 2 && n_mt != 4) || Lx > 64 || op.p_src0 < 0)
+        return fail_free("tensor-core executor: unsupported LinearAttention shape");
+      const int xi = op.p_src0 + 1;                       // image of x
+      const int Nq = (n_mt == 4) ? 64 : 128;              // columns per QKV slice: n_mt * Nq <= 256 accumulator columns
+      const size_t n_slots = 2 * (size_t)st->grid, rows_q = 128 * (size_t)n_mt;
+      float* scr[3] = {nullptr, nullptr, nullptr};
+      float* fold = nullptr;
+      for (int w = 0; w < 3; ++w) {
+        if (cudaMalloc(&scr[w], n_slots * rows_q * 128 * sizeof(float)) != cudaSuccess) return fail_free("out of memory (attention scratch)");
+        st->owned.push_back(reinterpret_cast<uint8_t*>(scr[w]));
+        st->activation_bytes += n_slots * rows_q * 128 * sizeof(float);
+      }
+      if (cudaMalloc(&fold, 768 * sizeof(float)) != cudaSuccess) return fail_free("out of memory (attention fold)");
+      st->owned.push_back(reinterpret_cast<uint8_t*>(fold));
+      attn_fold_kernel<<<3, 128, 0, stream>>>(net->blob + op.w, net->blob + op.gn_w, net->blob + op.gn_b, C, 384, fold, fold + 384);
+      // `out` of the core: 128 channels at this resolution.  With 4 m-tiles (7 samples at L = 64) the image would be 264 KB, more
+      // than the input buffers hold: two half-height images (rows 0..255 / 256..511 of the tile) and two to_out ops instead
+      const int n_half = (n_mt == 4) ? 2 : 1;
+      int oi[2] = {-1, -1};
+      for (int hf = 0; hf < n_half; ++hf) {
+        st->images.emplace_back();
+        oi[hf] = (int)st->images.size() - 1;
+        if (make_image(st->images[oi[hf]], 128, Lx, n_img, n_half == 2 ? 2 + 256 + 2 : 0) != MMDK_OK) return fail_free("out of memory (attention image)");
+      }
+      if (make_image(st->images[j + 1], C, Lx, n_img) != MMDK_OK) return fail_free("out of memory (activations)");
+      for (int sl = 0; sl < 384 / Nq; ++sl) {
+        st->ops.emplace_back();
+        FOp& p = st->ops.back();
+        p = FOp{};
+        p.kind = TC_ATTN_QKV; p.L = Lx; p.P = Lx + 2; p.n_mt = n_mt; p.N = Nq; p.cout = Nq; p.variant = FV_GENERIC; p.cond_off = -1;
+        p.src_C = C;
+        std::vector<HChunk> chunks;
+        uint32_t off = 0;
+        gemm_1x1(p, chunks, off, st->images[xi], net->blob + op.w, C, 384, sl * Nq, net->blob + op.gn_w);
+        p.bias = fold + 384 + sl * Nq;                    // u
+        p.gamma = fold + sl * Nq;                         // s
+        p.aux0 = scr[(sl * Nq) / 128] + (sl * Nq) % 128;
+        p.aux_ld = 128;
+        if (!finalize_op(p, chunks, off)) return fail_free(ferr);
+      }
+      {
+        st->ops.emplace_back();
+        FOp& p = st->ops.back();
+        p = FOp{};
+        p.kind = TC_ATTN_CORE; p.L = Lx; p.P = Lx + 2; p.n_mt = n_mt; p.N = 32; p.cout = 0; p.variant = FV_GENERIC; p.cond_off = -1;
+        p.aux0 = scr[0]; p.aux1 = scr[1]; p.aux2 = scr[2]; p.aux_ld = 128;
+        const TcImage& im = st->images[oi[0]];
+        p.out = im.dev; p.out_tile_bytes = im.tile_bytes; p.out_L = im.L; p.out_rows = im.rows; p.out_C = im.C;
+        if (n_half == 2) {
+          const TcImage& im2 = st->images[oi[1]];
+          p.out2 = im2.dev; p.out2_tile_bytes = im2.tile_bytes; p.out2_rows = im2.rows; p.out2_C = im2.C;
+        }
+        std::vector<HChunk> none;
+        if (!finalize_op(p, none, 0)) return fail_free(ferr);
+      }
+      for (int hf = 0; hf < n_half; ++hf) {
+        st->ops.emplace_back();
+        FOp& p = st->ops.back();
+        p = FOp{};
+        p.kind = TC_ATTN_OUT; p.L = Lx; p.P = Lx + 2; p.n_mt = n_mt / n_half; p.N = C; p.cout = C; p.variant = FV_GENERIC; p.cond_off = -1;
+        p.q_base = 256 * hf;
+        std::vector<HChunk> chunks;
+        uint32_t off = 0;
+        gemm_1x1(p, chunks, off, st->images[oi[hf]], net->blob + op.res_w, 128, C, 0, nullptr);
+        p.bias = net->blob + op.b;
+        const TcImage& ri = st->images[xi];
+        p.res_id = ri.dev; p.res_id_tile_bytes = ri.tile_bytes; p.res_id_rows = ri.rows; p.res_id_C = ri.C;
+        const TcImage& im = st->images[j + 1];
+        p.out = im.dev; p.out_tile_bytes = im.tile_bytes; p.out_L = im.L; p.out_rows = im.rows; p.out_C = im.C;
+        if (!finalize_op(p, chunks, off)) return fail_free(ferr);
+      }
+      continue;
+    }
+    st->ops.emplace_back();
+    FOp& p = st->ops.back();
     p = FOp{};
     p.kind = op.type == OP_CONVBLOCK ? TC_CONVBLOCK : op.type == OP_DOWN ? TC_DOWN : op.type == OP_UP ? TC_UP : TC_FINAL;
     p.L = op.lin; p.P = op.lin + 2;
@@ -923,7 +1184,6 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
       off += (st->images[img].tile_bytes + 127) & ~127u;
       return k;
     };
-    struct HChunk { uint32_t a_off, w_off, w_bytes; int d, acc, first, k16, slot; };
     std::vector<HChunk> chunks;
     auto add_chunks = [&](const std::vector<int>& imgs, int cin_total, int w_off_blob, int ktaps, int tap, int d, int acc,
                           bool first_in_acc) -> bool {
@@ -941,7 +1201,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
           cd.slot = slot;
           cd.w_bytes = (uint32_t)CK * p.N * 4;
           cd.w_off = w_total;
-          wsrc.push_back({net->blob + w_off_blob, cin_total, ktaps, tap, ci + c0, CK, op.cout, p.N, w_total});
+          wsrc.push_back({net->blob + w_off_blob, cin_total, ktaps, tap, ci + c0, CK, op.cout, p.N, w_total, 0, nullptr});
           w_total += cd.w_bytes;
           cd.d = d; cd.acc = acc; cd.first = first ? 1 : 0; cd.k16 = CK / 16;
           first = false;
@@ -974,23 +1234,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
       okc = okc && add_chunks(main_imgs, op.cin, op.w, 1, 0, 0, 0, true);
     }
     if (!okc) return fail_free("tensor-core executor: too many input images in one op");
-    p.in_bytes = off;
-    in_bytes[j] = off;
-    max_in = std::max(max_in, off);
-    p.chunk_base = (int)all_chunks.size();
-    p.n_chunks = (int)chunks.size();
-    // chunk weight offsets are relative to the op's base
-    op_w_off[j] = chunks.empty() ? w_total : chunks[0].w_off;
-    for (auto& cd : chunks) {
-      FChunk fc{};
-      const uint32_t lbo = p.src_lbo[cd.slot], plane = p.src_plane[cd.slot];
-      fc.a_w = (((cd.a_off + (uint32_t)((2 + cd.d) * 16)) >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
-      if (((2 * lbo) >> 4) > 0xFFFFu || (plane >> 4) > 0xFFFFu) return fail_free("tensor-core executor: image too large for the packed chunk descriptor");
-      fc.a_ks_pl = ((2 * lbo) >> 4) | ((plane >> 4) << 16);
-      fc.w_off = cd.w_off - op_w_off[j];
-      fc.meta = (uint32_t)cd.acc | ((uint32_t)cd.first << 1) | ((uint32_t)cd.k16 << 2);
-      all_chunks.push_back(fc);
-    }
+    if (!finalize_op(p, chunks, off)) return fail_free(ferr);
     p.bias = net->blob + op.b;
     p.cond_off = -1;
     if (p.kind == TC_CONVBLOCK) {
@@ -999,22 +1243,23 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
       p.cond_off = op.cond;
     }
   }
+  const int n_f = (int)st->ops.size();   // FOps (>= n_ops when the network has attention blocks)
   // shared-memory plan
   const uint32_t scratch = 2u * (F_MAX_N * 20) + 8u * F_PART_ROWS * 8u + 1024u + 8u * B_COUNT + 16u;
   const uint32_t avail = (uint32_t)max_smem - F_STAGES * F_STAGE_BYTES - scratch - 256u;
   uint32_t buf = 0;
-  for (int j = 0; j < n_ops; ++j) if (in_bytes[j] * 2 <= avail) buf = std::max(buf, in_bytes[j]);
+  for (int j = 0; j < n_f; ++j) if (in_bytes[j] * 2 <= avail) buf = std::max(buf, in_bytes[j]);
   buf = (buf + 127) & ~127u;
   if (buf == 0 || max_in > 2 * buf) {
     // the largest input needs both buffers: grow them as far as shared memory allows
     buf = std::max(buf, ((max_in + 1) / 2 + 127) & ~127u);
   }
   if (2 * buf > avail) return fail_free("tensor-core executor: an op's input images do not fit in shared memory");
-  for (int j = 0; j < n_ops; ++j) st->ops[j].big = in_bytes[j] > buf ? 1 : 0;
+  for (int j = 0; j < n_f; ++j) st->ops[j].big = in_bytes[j] > buf ? 1 : 0;
   // in-place hand-over (see FOp): conv block j -> op j + 1 when j + 1 reads nothing but j's output at the same resolution
-  for (int j = 0; j < n_ops; ++j) { st->ops[j].in_smem = 0; st->ops[j].out_smem = 0; st->ops[j].out_global = 1; }
+  for (int j = 0; j < n_f; ++j) { st->ops[j].in_smem = 0; st->ops[j].out_smem = 0; st->ops[j].out_global = 1; }
   const bool inplace_on = getenv("MMDK_FUSED_NO_INPLACE") == nullptr;
-  for (int j = 0; inplace_on && j + 1 < n_ops; ++j) {
+  for (int j = 0; inplace_on && j + 1 < n_f; ++j) {
     FOp& a = st->ops[j];
     FOp& b = st->ops[j + 1];
     if (a.kind != TC_CONVBLOCK || a.big || b.big || b.n_src != 1 || b.src[0] != a.out || b.L != a.out_L) continue;
@@ -1022,11 +1267,11 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
     a.out_smem = 1;
     b.in_smem = 1;
   }
-  for (int j = 0; j < n_ops; ++j) {
+  for (int j = 0; j < n_f; ++j) {
     FOp& a = st->ops[j];
     if (a.kind == TC_FINAL || !a.out) continue;
     bool needed = keep_all;
-    for (int m = j + 1; m < n_ops && !needed; ++m) {
+    for (int m = j + 1; m < n_f && !needed; ++m) {
       const FOp& b = st->ops[m];
       if (b.res_id == a.out) needed = true;
       if (!b.in_smem) for (int k = 0; k < b.n_src; ++k) if (b.src[k] == a.out) needed = true;
@@ -1047,13 +1292,13 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   if (cudaMalloc(&st->w_all, std::max<uint32_t>(w_total, 16)) != cudaSuccess) return fail_free("out of memory (packed weights)");
   for (const auto& w : wsrc)
     pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, w.cout, w.tap, w.ci0, w.CK, w.N,
-                                              reinterpret_cast<__half*>(st->w_all + w.dst_off));
-  for (int j = 0; j < n_ops; ++j) st->ops[j].wchunks = st->w_all + op_w_off[j];
-  if (n_ops > F_MAX_OPS || all_chunks.size() + 1 > (size_t)F_MAX_CHUNKS) return fail_free("tensor-core executor: layer program too large for the parameter bank");
+                                              reinterpret_cast<__half*>(st->w_all + w.dst_off), w.n0, w.scale);
+  for (int j = 0; j < n_f; ++j) st->ops[j].wchunks = st->w_all + op_w_off[j];
+  if (n_f > F_MAX_OPS || all_chunks.size() + 1 > (size_t)F_MAX_CHUNKS) return fail_free("tensor-core executor: layer program too large for the parameter bank");
   if (check_cuda(cudaGetLastError(), "tensor-core executor setup") != MMDK_OK) { fused_free(st); return MMDK_ECUDA; }
-  for (int j = 0; j < n_ops; ++j) P.ops[j] = st->ops[j];
+  for (int j = 0; j < n_f; ++j) P.ops[j] = st->ops[j];
   for (size_t c = 0; c < all_chunks.size(); ++c) P.chunks[c] = all_chunks[c];
-  P.n_ops = n_ops;
+  P.n_ops = n_f;
   P.n_tiles = st->n_tiles;
   P.B = B;
   P.st = st->st;

@@ -141,9 +141,10 @@ class TemporalUnet(nn.Module):
         self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._invalidate())
 
     def tensor_core_supported(self):
-        """Whether the tcgen05 executor covers this network shape (unet_tc.cu build_tc): no LinearAttention, and every
-        level's (rows of a 7-sample tile) x channels fits the epilogue's register tiling."""
-        if self.self_attention or self.state_dim > 8:
+        """Whether the tcgen05 executor covers this network shape (unet_fused.cu build_fused): every level's (rows of a
+        7-sample tile) x channels fits the epilogue's register tiling.  LinearAttention blocks are covered (QKV / out
+        projections as tensor-core GEMMs)."""
+        if self.state_dim > 8:
             return False
         L = self.n_support_points
         for i, m in enumerate(self.dim_mults):

@@ -92,7 +92,7 @@ def test_executor_selection():
     assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4)).resolve_precision() == "f16x3"
     assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4, 8)).resolve_precision() == "fp32"
     assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4),
-                          self_attention=True).resolve_precision() == "fp32"
+                          self_attention=True).resolve_precision() == "f16x3"   # LinearAttention runs on the tcgen05 executor too
     u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4), unet_precision="fp32")
     assert u.resolve_precision() == "fp32" and u.resolve_precision("f16x3") == "f16x3"
 
