@@ -21,13 +21,21 @@ def _worker(rank, world, port, n_total, q):
     dist.destroy_process_group()
 
 
-def _run(n_total, port):
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(n_total, port=None):
+    port = port or _free_port()   # a fixed port collides with leftovers of earlier runs on a busy box
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     return sorted(res, key=lambda t: t[0])
@@ -41,7 +49,7 @@ def test_shard_robots_partitions_contiguously():
 
 
 def test_all_gather_of_representative_paths_even():
-    res = _run(8, 29611)
+    res = _run(8)
     want = torch.stack([torch.full((64, 2), float(r)) + torch.arange(64)[:, None] * 1e-3 for r in range(8)])
     for rank, lo, hi, out in res:
         assert (lo, hi) == (rank * 4, rank * 4 + 4)
@@ -49,7 +57,7 @@ def test_all_gather_of_representative_paths_even():
 
 
 def test_all_gather_of_representative_paths_ragged():
-    res = _run(5, 29612)
+    res = _run(5)
     want = torch.stack([torch.full((64, 2), float(r)) + torch.arange(64)[:, None] * 1e-3 for r in range(5)])
     for rank, lo, hi, out in res:
         assert torch.equal(out, want)
