@@ -5,7 +5,8 @@ Default workload = BASELINE.json config 4: EnvHighways2D, 32 robots x 128 sample
 horizon 64, full guidance (SDF collision + workspace border + GP smoothness + lock-step inter-robot soft constraints, 20 guide
 steps for t < 50), UNet dim_mults (1,2,4) with seeded random-init weights, synthetic SmallCircle starts/goals
 (mmd/config/mmd_experiment_configs.py:142-156).  One "step" = one complete reverse chain for the whole batch.  --config 1|2|3
-select the smaller BASELINE.json configurations (parity-test cases; their lines are kept under profiles/).
+select the smaller BASELINE.json configurations (parity-test cases; their lines are kept under profiles/); --config 5 is the
+MPDEnsemble 1x2 multi-tile configuration (one multi-tile planner per robot, all robots served by mmd_b200.plan_batch).
 
 N > 1 (torchrun, one rank per GPU), --scaling:
   strong (default; BASELINE.json: "32 robots x 128 samples ... batch sharded across 8xB200"): the SAME fleet, robots sharded
@@ -47,6 +48,8 @@ CONFIGS = {
     2: dict(env="EnvEmpty2D", R=6, K=32, T=100, name="config 2: Empty map, 6 robots x 32 samples, 100 steps"),
     3: dict(env="EnvConveyor2D", R=10, K=64, T=100, name="config 3: Conveyor map, 10 robots x 64 samples, 100 steps"),
     4: dict(env="EnvHighways2D", R=32, K=128, T=100, name="config 4: Highways map, 32 robots x 128 samples, 100 steps"),
+    5: dict(env="EnvEmptyNoWait2D", R=16, K=64, T=100, tiles=2,
+            name="config 5: MPDEnsemble 1x2 multi-tile, 16 robots x 64 samples, 100 steps"),
 }
 
 
@@ -110,17 +113,19 @@ def cpu_sample(cfg, n_robots_total, budget_s=25.0):
     setting the MEDIAN of 3 guided steps and of 3 unguided steps (after one warm-up step); the best setting is reported."""
     from oracle import port
     env, K, T = cfg["env"], cfg["K"], cfg["T"]
+    n_tiles = cfg.get("tiles", 1)
     P = port.make_unet_params(seed=0)
     sdf, grad = port.build_sdf_grid(env)
     norm = port.LimitsNormalizer(*port.DEFAULT_NORMALIZER_LIMITS)
-    guide = port.GuideSpec(port.GridSDF(sdf, grad), norm)
+    guide = port.GuideSpec(port.GridSDF(sdf, grad), norm, cutoff_margin=0.01 if n_tiles > 1 else 0.05)   # mpd_ensemble.py:139 / mpd.py:127
     model = port.DiffusionModel(P, T)
     starts, goals = small_circle(n_robots_total)
     g = torch.Generator().manual_seed(18)
     hc = port.repeat_hard_conds(port.hard_conds_from_start_goal(starts[0], goals[0], norm), K)
     x = port.apply_hard_conditioning(torch.randn(K, H, D, generator=g), hc)
-    # peers: straight-line paths of the other robots (positions only matter for the cost of the evaluation)
-    if n_robots_total > 1:
+    # peers: straight-line paths of the other robots (positions only matter for the cost of the evaluation); the multi-tile
+    # configuration is the CBS root pattern (one unconstrained planner call per robot, cbs.py:316-324)
+    if n_robots_total > 1 and n_tiles == 1:
         tt = torch.linspace(0, 1, H)[:, None]
         qs = torch.cat([starts[j][None] * (1 - tt) + goals[j][None] * tt for j in range(1, n_robots_total)], 0)
         hh = torch.arange(H, dtype=torch.float32).repeat(n_robots_total - 1)
@@ -144,15 +149,17 @@ def cpu_sample(cfg, n_robots_total, budget_s=25.0):
         step(T - 1)  # warm-up (thread pool, allocator)
         tu = statistics.median(step(T - 1 - i) for i in range(3))
         tg = statistics.median(step(10 + i) for i in range(3))
-        per_robot = n_u * tu + n_g * tg
+        per_robot = n_tiles * (n_u * tu + n_g * tg)   # an ensemble steps every tile model once per reverse step (diffusion_ensemble.py:86-101)
         tried.append((nt, round(tg, 3)))
         if best is None or per_robot < best[3]:
             best = (nt, tu, tg, per_robot)
         if time.perf_counter() - t_begin > budget_s:
             break
     nt, tu, tg, per_robot = best
-    sample = (f"oracle/port.py (bit-exact restatement of the reference on CPU), robot 0 of {n_robots_total} (K={K}) with "
-              f"{n_robots_total - 1} peer paths = {(n_robots_total - 1) * H} soft vertex constraints: median of 3 -> "
+    n_peer = (n_robots_total - 1) if n_tiles == 1 else 0
+    sample = (f"oracle/port.py (bit-exact restatement of the reference on CPU), robot 0 of {n_robots_total} (K={K}"
+              f"{', one tile of %d; per-robot time = %d x one tile' % (n_tiles, n_tiles) if n_tiles > 1 else ''}) with "
+              f"{n_peer} peer paths = {n_peer * H} soft vertex constraints: median of 3 -> "
               f"{tu * 1e3:.0f} ms per unguided reverse step, {tg:.2f} s per guided step (20 guide evaluations), best of the thread "
               f"sweep {tried} (threads, guided s) = {nt} threads; extrapolated to {n_u} unguided + {n_g} guided steps; robots run "
               f"sequentially on the CPU as in cbs.py:316-324, so traj/s = K / per-robot chain time ({per_robot:.1f} s)")
@@ -178,6 +185,16 @@ def run_reference(args):
 
 
 def workload_config(cfg, n_gpus, scaling):
+    if cfg.get("tiles", 1) > 1:
+        T = cfg["T"]
+        return {"workload": f"BASELINE.json {cfg['name']}; tiles {cfg['env']} with transforms (0,0),(2,0) (inference_multi_agent.py:146-149), "
+                            f"{cfg['R']} MPDEnsemble planners (skeletons alternating tile 0->1 / 1->0) x {cfg['K']} samples, each trajectory = "
+                            f"{cfg['tiles']} x {H} waypoints stitched by cross conditioning; T={T}+{N_EXTRA} reverse steps x {cfg['tiles']} tile "
+                            f"models per step, {N_GUIDE} guide steps for t<{math.ceil(0.5 * T)}; CBS root pattern (no inter-robot constraints)",
+                "robots_total": cfg["R"], "robots_per_gpu": cfg["R"], "samples": cfg["K"], "ddpm_steps": T, "horizon": H,
+                "tiles": cfg["tiles"], "unet_dim_mults": [1, 2, 4],
+                "parallelism": "single GPU; all planner calls of the root loop in one batch per tile model (mmd_b200.plan_batch)",
+                "l2": "chain frames + noise (2 tiles x 102 frames x 1 MiB x 2) exceed the 126 MB L2; no explicit flush"}
     R_total = cfg["R"] * (n_gpus if scaling == "weak" else 1)
     per = (R_total + n_gpus - 1) // n_gpus
     T = cfg["T"]
@@ -256,7 +273,7 @@ def run_gpu(args):
     STAMP_SLOTS = 256
     stamps = torch.zeros(STAMP_SLOTS, n_sm, 2, dtype=torch.int64, device=dev)
     unet.ensure_time_table(T)
-    fused = unet.resolve_precision(args.precision) == "f16x3"
+    fused = unet.native_mode(args.precision) == _lib.UNET_F16X3
     if fused:
         _lib.check(_lib.lib().mmdk_unet_debug_stamps(unet.native(), _lib.ptr(stamps), STAMP_SLOTS, n_sm))
 
@@ -391,6 +408,121 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_ensemble(args):
+    """BASELINE config 5: one MPDEnsemble (1x2 tiles) planner per robot.  value = the batched multi-tile chain alone (noise
+    resident, CUDA events); e2e = mmd_b200.plan_batch(planners) from host start/goal states to the planners' smoothed final
+    trajectories on the host; e2e_planner = the reference's own pattern, the planners called one after the other."""
+    import mmd_b200 as M
+    from mmd_b200 import _lib, planners as PL
+    from oracle import port
+    cfg = CONFIGS[args.config]
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("config 5 is benchmarked on one GPU (independent planner calls: more GPUs = independent replicas)")
+    K, T, R, NT = cfg["K"], cfg["T"], cfg["R"], cfg["tiles"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    unet = M.TemporalUnet(n_support_points=H, state_dim=D, unet_input_dim=32, dim_mults=(1, 2, 4), unet_precision=args.precision)
+    unet.load_state_dict(port.make_unet_params(seed=0), strict=True)
+    model = M.GaussianDiffusionModel(model=unet, variance_schedule="exponential", n_diffusion_steps=T, predict_epsilon=True).to(dev)
+    models = {j: model for j in range(NT)}   # the reference loads the same checkpoint once per tile (inference_multi_agent.py:205-222)
+    tile_tf = [torch.tensor([2.0 * j, 0.0]) for j in range(NT)]
+    s_loc, g_loc = port.get_start_goal_pos_circle(R, 0.8)
+    planners, sg = [], []
+    for r in range(R):
+        skel = list(range(NT)) if r % 2 == 0 else list(reversed(range(NT)))
+        tr = {j: tile_tf[skel[j]] for j in range(NT)}
+        start, goal = s_loc[r] + tile_tf[skel[0]], g_loc[r] + tile_tf[skel[-1]]
+        planners.append(M.MPDEnsemble((cfg["env"] + "-RobotPlanarDisk",) * NT, tr, "mmd", start, goal, n_samples=K, models=models,
+                                      device=str(dev)))
+        sg.append(torch.stack((start, goal)))
+    sg_host = torch.stack(sg).pin_memory()
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    STAMP_SLOTS = 512
+    stamps = torch.zeros(STAMP_SLOTS, n_sm, 2, dtype=torch.int64, device=dev)
+    unet.ensure_time_table(T)
+    fused = unet.native_mode(args.precision) == _lib.UNET_F16X3
+    if fused:
+        _lib.check(_lib.lib().mmdk_unet_debug_stamps(unet.native(), _lib.ptr(stamps), STAMP_SLOTS, n_sm))
+    result_host = torch.empty(R, K, NT * H, D).pin_memory()
+
+    def step():
+        s_g = sg_host.to(dev, non_blocking=True)
+        outs = M.plan_batch(planners, None, rng="batched", starts_goals=s_g)
+        for r, o in enumerate(outs):
+            result_host[r].copy_(o.trajs_final, non_blocking=True)
+        return outs
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    stamps.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    chain_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        outs = step()
+        chain_ms.append(PL.last_batch_chain_ms())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    clk = clocks.stop()
+    ms_chain = sum(chain_ms) / len(chain_ms)
+    B = R * K
+    n_steps = T + N_EXTRA
+    if fused:
+        spt = 1 if B <= n_sm else (3 if B <= 3 * n_sm else 7)
+        grid = min((B + spt - 1) // spt, n_sm)
+        st = stamps[:, :grid].cpu()
+        live = (st[:, :, 0] > 0).all(dim=1) & (st[:, :, 1] > 0).all(dim=1)
+        dur_ns = (st[:, :, 1].max(dim=1).values - st[:, :, 0].min(dim=1).values)[live].double()
+        unet_ms = (dur_ns / 1e6).tolist()
+    else:
+        unet_ms = [float("nan")]
+    unet_avg_ms = sum(unet_ms) / len(unet_ms)
+    # the reference's pattern: sequential planner calls
+    torch.cuda.synchronize()
+    planners[0](planners[0].start_state_pos, planners[0].goal_state_pos)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for p in planners:
+        p(p.start_state_pos, p.goal_state_pos)
+    torch.cuda.synchronize()
+    dt_seq = time.perf_counter() - t0
+    pk, pk_kind = peaks()
+    achieved = B * UNET_FLOP_PER_SAMPLE / (unet_avg_ms / 1e3) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb_v, nt, sample, _ = cpu_sample(cfg, R)
+        cpu = {"value": cb_v, "unit": "trajectories/s", "cores": nt, "kind": "port", "sample": sample, "host_cores": os.cpu_count()}
+    n_guided = math.ceil(0.5 * T) + N_EXTRA
+    line = {
+        "metric": "denoised trajectories/sec", "value": B / (ms_chain / 1e3), "unit": "trajectories/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_chain, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16x3", "data": "synthetic",
+        "config": workload_config(cfg, 1, args.scaling),
+        "finite": bool(all(torch.isfinite(o.trajs_final).all() for o in outs)),
+        "note": f"one trajectory = {NT} tiles x {H} waypoints = {NT} UNet forwards per reverse step; tile-trajectories/s = {NT} x value",
+        "e2e": {"value": B / (ms_e2e / 1e3), "unit": "trajectories/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(sg_host.numel() * 4), "d2h_bytes_per_step": int(result_host.numel() * 4),
+                "note": "mmd_b200.plan_batch(planners): noise drawn on the device, batched chain, per-planner post-processing "
+                        "(unnormalise, classify, stitch tiles, best trajectory, Savitzky-Golay), final trajectories D2H"},
+        "e2e_planner": {"value": B / dt_seq, "unit": "trajectories/s", "calls": R, "ms_per_call": 1e3 * dt_seq / R,
+                        "note": "sequential MPDEnsemble.__call__(start, goal) -> PlannerOutput (cbs.py:316-324)"},
+        # per tile step: pack_input + persistent forward + ddpm_step + one cross-conditioning launch per transform set (2)
+        "gpu_launches": args.steps * (n_steps * NT * ((2 if fused else 1) + 1 + 2) + 2),
+        "roofline": {"bound": "tensor", "kernel": "TemporalUnet forward (" + args.precision + ")", "achieved": achieved,
+                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                     "traffic": None, "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
+                     "algorithmic_flop_per_launch": B * UNET_FLOP_PER_SAMPLE, "avg_launch_ms": unet_avg_ms,
+                     "unet_share_of_step": unet_avg_ms * n_steps * NT / ms_chain, "forwards_timed": len(unet_ms),
+                     "timing": "%globaltimer stamps written by every CTA of every forward of the last timed chain"},
+        "cpu_baseline": cpu, "clocks": clk,
+    }
+    print(json.dumps(line))
+
+
 def planner_bench(M, model, env_name, ta, starts, goals, K, n_calls):
     """The reference's call pattern (cbs.py:316-324): one MPD planner object per robot (mpd.py:64-88), called one after the
     other; each call = full guided chain for K samples + the planner's post-processing."""
@@ -443,6 +575,8 @@ def main():
         args.warmup = 3   # timing rule: at least 3 untimed chains
     if args.impl == "reference":
         run_reference(args)
+    elif CONFIGS[args.config].get("tiles", 1) > 1:
+        run_gpu_ensemble(args)
     else:
         run_gpu(args)
 

@@ -15,7 +15,7 @@ constexpr int MAX_W_STAGES = 3;
 constexpr int TC_THREADS = 320;
 constexpr int TMEM_COLS = 256;
 constexpr int MAX_SRC = 4;
-constexpr int MAX_CHUNKS = 48;
+constexpr int MAX_CHUNKS = 96;   // 5 taps x 16 (32-channel) chunks + 16 residual chunks: the 512-channel concat block of the 4-level net
 constexpr int TC_CLUSTER = 1;    // >1: CTAs per cluster sharing every weight chunk through TMA multicast.  Measured on B200 (r01): the main
                                  // loop is tensor-pipe bound (two resident CTAs share the pipe), not L2 bound, and 4-CTA clusters cost
                                  // scheduling tails (1.85 vs 1.29 ms per forward) -> off by default, code path kept.
@@ -30,6 +30,7 @@ struct ChunkDesc {
   int acc;           // accumulator region (0: columns [0,128), 1: [128,256))
   int first;         // first chunk accumulated into this region
   int k16;           // 16-channel K steps in this chunk (1 or 2)
+  int phase;         // input phase this chunk reads (two-phase ops reload the input buffer between phases)
 };
 
 enum TcKind : int { TC_CONVBLOCK = 0, TC_DOWN = 1, TC_UP = 2, TC_FINAL = 3, TC_ATTN_QKV = 4, TC_ATTN_CORE = 5, TC_ATTN_OUT = 6 };
@@ -40,6 +41,10 @@ struct TcOpParams {
   uint32_t src_tile_bytes[MAX_SRC];
   uint32_t src_smem_off[MAX_SRC];
   int n_src;
+  int src_phase[MAX_SRC];   // input phase that loads this source (all 0 unless the sources do not fit shared memory together)
+  int n_phase;              // 1, or 2: phase 1's sources overwrite phase 0's once its MMAs have completed
+  int n_split;              // output channels cut into n_split slices of N (gridDim.y): slice s owns channels [s N, (s + 1) N)
+  uint32_t w_split_bytes;   // packed weight bytes per slice
   const uint8_t* wchunks;
   int n_chunks;
   uint32_t w_stage_bytes;

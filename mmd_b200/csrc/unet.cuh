@@ -20,7 +20,8 @@ struct UnetImpl {
   int per_sample_floats = 0;    // activation floats per sample for the fp32 executor
   int ffma_S = 1;               // samples per CTA of the fp32 executor
   int attn_scratch_floats = 0;  // shared scratch of the LinearAttention op (qkv + context + stats), 0 without attention
-  TcState* tc = nullptr;
+  TcState* tc = nullptr;              // per-layer executor state of the last batch size used
+  std::map<int, TcState*> tc_cache;   // per batch size (bounded; see unet_forward_tc)
   std::map<int, FusedState*> fused;   // per batch size (bounded; see unet_forward_fused)
   FusedState* fused_last = nullptr;
   int last_mode = 0;

@@ -15,6 +15,7 @@
 // with M = 128 rows per MMA (n_mt MMAs tiles per image), N = cout, K = 16 per instruction.
 // Images move global<->shared with bulk async copies (TMA, UBLKCP) completing on mbarriers; weights stream through a
 // 3-stage ring; one elected thread issues tcgen05.mma; four warps run the epilogue straight out of TMEM.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -31,7 +32,7 @@ namespace {
 // warp 9: bulk-copy producer.  __launch_bounds__(320, 2): two CTAs per SM so that one CTA's epilogue (CUDA cores)
 // overlaps the other's loads + MMAs (tensor pipe).
 // ------------------------------------------------------------------------------------------------------------------
-template <int NV, int N>
+template <int NV, int N, int NG>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcOpParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NMT = NV / N;
@@ -39,6 +40,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   constexpr int NVH = NMT * NH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x;
+  // blockIdx.y = output-channel slice (256-channel layers of the 4-level net: two slices of N = 128, four GroupNorm groups each --
+  // groups are channel-contiguous, so a slice is a self-contained conv block over the same input)
+  const int col0 = (int)blockIdx.y * N;
+  const uint8_t* const wchunks = p.wchunks + (size_t)blockIdx.y * p.w_split_bytes;
   const int CS = p.cluster;
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
@@ -47,7 +52,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   const uint32_t bar_base = smem_base + p.smem_bar_off;
   // barriers: [0] in_full, [1..3] w_full, [4..6] w_empty, [7] acc_full ; then the TMEM base pointer
   const uint32_t bar_in = bar_base, bar_wfull = bar_base + 8, bar_wempty = bar_base + 8 + 8 * MAX_W_STAGES,
-                 bar_acc = bar_base + 8 + 16 * MAX_W_STAGES;
+                 bar_acc = bar_base + 8 + 16 * MAX_W_STAGES, bar_in_empty = bar_acc + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + p.smem_bar_off + 8 + 16 * MAX_W_STAGES + 8);
   const int WS = p.w_stages;
 
@@ -55,6 +60,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     mbar_init(bar_in, 1);
     for (int s = 0; s < MAX_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, (uint32_t)CS); }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_in_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -83,35 +89,47 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
         if (CS > 1) {
           const uint32_t part = cd.w_bytes / (uint32_t)CS, po = crank * part;
-          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, p.wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
+          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
         } else {
-          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
         }
         if (++st == WS) { st = 0; ph ^= 1; }
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");
       MMDK_STAMP(1);
-      uint32_t total = 0;
-      for (int s = 0; s < p.n_src; ++s) total += p.src_tile_bytes[s];
-      mbar_expect_tx(bar_in, total);
-      for (int s = 0; s < p.n_src; ++s) {
-        const uint8_t* g = p.src[s] + (size_t)tile_ld * p.src_tile_bytes[s];
-        uint32_t off = 0;
-        while (off < p.src_tile_bytes[s]) {
-          uint32_t n = min(p.src_tile_bytes[s] - off, 32768u);
-          bulk_g2s(smem_base + p.src_smem_off[s] + off, g + off, n, bar_in);
-          off += n;
+      auto load_inputs = [&](int phase) {
+        uint32_t total = 0;
+        for (int s = 0; s < p.n_src; ++s) if (p.src_phase[s] == phase) total += p.src_tile_bytes[s];
+        mbar_expect_tx(bar_in, total);
+        for (int s = 0; s < p.n_src; ++s) {
+          if (p.src_phase[s] != phase) continue;
+          const uint8_t* g = p.src[s] + (size_t)tile_ld * p.src_tile_bytes[s];
+          uint32_t off = 0;
+          while (off < p.src_tile_bytes[s]) {
+            uint32_t n = min(p.src_tile_bytes[s] - off, 32768u);
+            bulk_g2s(smem_base + p.src_smem_off[s] + off, g + off, n, bar_in);
+            off += n;
+          }
         }
-      }
+      };
+      load_inputs(0);
+      int in_phase = 0;
+      // chunks already in the ring belong to phase 0 (the builder keeps >= MAX_W_STAGES chunks per phase)
       for (int c = c_pre; c < p.n_chunks; ++c) {
         mbar_wait(bar_wempty + 8 * st, ph ^ 1);
         const ChunkDesc cd = p.chunks[c];
+        if (cd.phase != in_phase) {
+          // the MMA warp commits bar_in_empty after the last MMA that reads the previous phase's input buffer
+          mbar_wait(bar_in_empty, (uint32_t)(in_phase & 1));
+          in_phase = cd.phase;
+          load_inputs(in_phase);
+        }
         mbar_expect_tx(bar_wfull + 8 * st, cd.w_bytes);
         if (CS > 1) {
           const uint32_t part = cd.w_bytes / (uint32_t)CS, po = crank * part;
-          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, p.wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
+          bulk_g2s_mc(smem_base + p.smem_w_off + st * p.w_stage_bytes + po, wchunks + cd.w_off + po, part, bar_wfull + 8 * st, cmask);
         } else {
-          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, p.wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
+          bulk_g2s(smem_base + p.smem_w_off + st * p.w_stage_bytes, wchunks + cd.w_off, cd.w_bytes, bar_wfull + 8 * st);
         }
         if (++st == WS) { st = 0; ph ^= 1; }
       }
@@ -124,9 +142,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(bar_in, 0);
       MMDK_STAMP(3);
-      int st = 0, ph = 0;
+      int st = 0, ph = 0, in_phase = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         const ChunkDesc cd = p.chunks[c];
+        if (cd.phase != in_phase) {
+          tc_commit(bar_in_empty);                 // arrives once every MMA issued so far has read its operands
+          in_phase = cd.phase;
+          mbar_wait(bar_in, (uint32_t)(in_phase & 1));
+          tc_fence_after();
+        }
         mbar_wait(bar_wfull + 8 * st, ph);
         tc_fence_after();
         const uint32_t wbase = smem_base + p.smem_w_off + st * p.w_stage_bytes;
@@ -169,9 +193,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     // stage the per-channel parameters while the MMAs run
     if (tid < N) {
-      prm4[tid] = make_float4((tid < p.cout) ? __ldg(p.bias + tid) : 0.f, p.gamma ? __ldg(p.gamma + tid) : 1.f,
-                              p.beta ? __ldg(p.beta + tid) : 0.f, p.cond ? __ldg(p.cond + tid) : 0.f);
-      prm_rb[tid] = p.res_bias ? __ldg(p.res_bias + tid) : 0.f;
+      const int cg = col0 + tid;   // global output channel
+      prm4[tid] = make_float4((cg < p.cout) ? __ldg(p.bias + cg) : 0.f, p.gamma ? __ldg(p.gamma + cg) : 1.f,
+                              p.beta ? __ldg(p.beta + cg) : 0.f, p.cond ? __ldg(p.cond + cg) : 0.f);
+      prm_rb[tid] = p.res_bias ? __ldg(p.res_bias + cg) : 0.f;
     }
     epi_bar();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // outputs / residual reads only after the previous grid is complete
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 
     if (p.kind == TC_CONVBLOCK) {
       if constexpr (N >= 32) {
-        constexpr int CPG = N / 8;                 // channels per group
+        constexpr int CPG = N / NG;                // channels per group (NG groups inside this CTA's N columns)
         constexpr int GB = (CPG > 8) ? CPG : 8;    // columns per statistics block
         // ---- GroupNorm statistics: per-row (sum, M2) -> one exchange -> Chan's combination (stable, 2 barriers)
 #pragma unroll 1
@@ -194,7 +219,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           for (int gb = 0; gb < NH / GB; ++gb) {
             float w[GB];
             const int cb = c0 + gb * GB;
-            if constexpr (GB == 16) tmem_ld16(lane_base + i * N + cb, w); else tmem_ld8(lane_base + i * N + cb, w);
+            if constexpr (GB == 32) tmem_ld32(lane_base + i * N + cb, w);
+            else if constexpr (GB == 16) tmem_ld16(lane_base + i * N + cb, w);
+            else tmem_ld8(lane_base + i * N + cb, w);
             tmem_wait_ld();
 #pragma unroll
             for (int e = 0; e < GB; ++e) w[e] += prm4[cb + e].x;
@@ -214,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         if (tid == 0) MMDK_STAMP(7);
         epi_bar();
         if (tid == 0) MMDK_STAMP(8);
-        if (tid < ST * 8) {
+        if (tid < ST * 8 && (tid & 7) < NG) {
           const int sidx = tid >> 3, g = tid & 7;
           const float inv_n = 1.f / (float)(CPG * L);
           float sum = 0.f;
@@ -244,8 +271,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           const uint8_t* rbase = (p.res_id && ok) ? p.res_id + (size_t)tile * p.res_id_tile_bytes + (size_t)r * 16 : nullptr;
           uint4 rh = make_uint4(0, 0, 0, 0), rl = rh;
           if (rbase) {
-            rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16));
-            rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(c0 / 8) * p.res_id_rows * 16 + rplane));
+            rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)((col0 + c0) / 8) * p.res_id_rows * 16));
+            rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)((col0 + c0) / 8) * p.res_id_rows * 16 + rplane));
           }
           uint8_t* obase = p.out + (size_t)tile * p.out_tile_bytes + (size_t)r * 16;
 #pragma unroll 1
@@ -253,8 +280,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             const int cb = c0 + pc * 8;          // first channel of this panel
             const uint4 ch = rh, cl = rl;
             if (rbase && pc + 1 < NH / 8) {
-              rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(cb / 8 + 1) * p.res_id_rows * 16));
-              rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(cb / 8 + 1) * p.res_id_rows * 16 + rplane));
+              rh = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)((col0 + cb) / 8 + 1) * p.res_id_rows * 16));
+              rl = __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)((col0 + cb) / 8 + 1) * p.res_id_rows * 16 + rplane));
             }
             float y[8], r1[8];
             tmem_ld8(lane_base + i * N + cb, y);
@@ -276,7 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
               if (rbase) add8(ch, cl, y);
               uint4 hi, lo;
               split8(y, hi, lo);
-              uint8_t* ob = obase + (size_t)(cb / 8) * p.out_rows * 16;
+              uint8_t* ob = obase + (size_t)((col0 + cb) / 8) * p.out_rows * 16;
               *reinterpret_cast<uint4*>(ob) = hi;
               *reinterpret_cast<uint4*>(ob + oplane) = lo;
             }
@@ -412,7 +439,7 @@ __global__ void __launch_bounds__(128, 1) mma_calibrate_kernel(int N, int n_iter
 // ------------------------------------------------------------------------------------------------------------------
 struct TcOpHost {
   TcOpParams prm{};
-  int NV = 0, N = 0;
+  int NV = 0, N = 0, NG = 8;
   size_t smem = 0;
   uint8_t* w_dev = nullptr;
   int cond_off = -1;
@@ -433,19 +460,25 @@ static void tc_free(TcState* s) {
 }
 
 void unet_tc_release(UnetImpl* net) {
-  if (net && net->tc) { tc_free(net->tc); net->tc = nullptr; }
+  if (!net) return;
+  for (auto& kv : net->tc_cache) tc_free(kv.second);
+  net->tc_cache.clear();
+  net->tc = nullptr;
 }
 
-template <int NV, int N>
+template <int NV, int N, int NG>
 static int launch_tc(const TcOpHost& o, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (o.smem > configured) {
-    MMDK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NV, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = 232448;
+  static bool configured[64] = {};   // the attribute is per device (and per template instantiation)
+  int dev = 0;
+  MMDK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(MMDK_EINVAL, "device index out of range");
+  if (!configured[dev]) {
+    MMDK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NV, N, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   const int cs = o.prm.cluster;
-  cfg.gridDim = dim3((unsigned)(((o.prm.n_tiles + cs - 1) / cs) * cs));
+  cfg.gridDim = dim3((unsigned)(((o.prm.n_tiles + cs - 1) / cs) * cs), (unsigned)o.prm.n_split);
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = o.smem;
   cfg.stream = stream;
@@ -462,7 +495,7 @@ static int launch_tc(const TcOpHost& o, cudaStream_t stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NV, N>, o.prm), "conv_tc_kernel launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NV, N, NG>, o.prm), "conv_tc_kernel launch");
 }
 
 static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
@@ -496,12 +529,19 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     p.n_mt = (p.rows - 4) / 128;
     p.cout = op.cout;
     p.N = op.cout < 16 ? 16 : op.cout;
+    p.n_split = 1;
+    if (op.cout == 256 && op.type == OP_CONVBLOCK) {   // dim_mults (1,2,4,8): two slices of 128 channels = 4 GroupNorm groups each
+      p.N = 128;
+      p.n_split = 2;
+    }
     if (p.N != 16 && p.N != 32 && p.N != 64 && p.N != 128) return fail_free("tensor-core executor: unsupported channel count");
     h.N = p.N;
+    h.NG = 8 / p.n_split;
     h.NV = p.n_mt * p.N;
     if (!((h.NV == 128 && (p.N == 32 || p.N == 64 || p.N == 128)) || (h.NV == 64 && (p.N == 64 || p.N == 32 || p.N == 16))))
       return fail_free("tensor-core executor: unsupported (rows, channels) combination for this network shape");
     if (p.kind == TC_CONVBLOCK && op.n_groups != 8) return fail_free("tensor-core executor: GroupNorm needs 8 groups");
+    if (p.n_split > 1 && h.NV != 128) return fail_free("tensor-core executor: 256-channel layers need a single 128-row m-tile");
     p.B = B; p.n_tiles = st->n_tiles;
     // output image
     if (p.kind != TC_FINAL) {
@@ -522,14 +562,37 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
       res_imgs.push_back(img_of(op.p_res));
       if (op.p_res1 > -2) res_imgs.push_back(img_of(op.p_res1));
     }
-    uint32_t off = 0;
+    // every source image of the op resident at once, or -- when they do not fit (4-level net: the 512-channel concat at L = 8
+    // is 2 x 135 KB, and the block that adds its 1x1 residual conv reads a third image) -- STREAMED: one image per input
+    // phase through the same buffer (phase k + 1 is loaded once the MMAs of phase k have completed)
+    std::vector<int> distinct;
+    uint32_t all_src_bytes = 0, max_src_bytes = 0;
+    for (const std::vector<int>* v : {&main_imgs, &res_imgs})
+      for (int img : *v)
+        if (std::find(distinct.begin(), distinct.end(), img) == distinct.end()) {
+          distinct.push_back(img);
+          const uint32_t b = (st->images[img].tile_bytes + 127) & ~127u;
+          all_src_bytes += b;
+          max_src_bytes = std::max(max_src_bytes, b);
+        }
+    const uint32_t scratch = (uint32_t)(5 * p.N + p.n_mt * 128 * 8 * 2 + 2 * ST * 8) * 4;
+    const uint32_t tail = ((scratch + 15) & ~15u) + 8 + 16 * MAX_W_STAGES + 8 + 16;
+    const uint32_t ring = (uint32_t)MAX_W_STAGES * 32u * (uint32_t)p.N * 4u;
+    const bool streamed = all_src_bytes + ring + tail > 232448u;
+    if (streamed && (p.kind != TC_CONVBLOCK || max_src_bytes + ring + tail > 232448u || distinct.size() > (size_t)MAX_SRC))
+      return fail_free("tensor-core executor: input images do not fit in shared memory");
+    p.n_phase = streamed ? (int)distinct.size() : 1;
+    uint32_t off = 0, off_phase[MAX_SRC] = {0, 0, 0, 0};
+    int cur_phase = 0;
     auto add_src = [&](int img) -> int {
       for (int k = 0; k < p.n_src; ++k) if (p.src[k] == st->images[img].dev) return k;
       int k = p.n_src++;
       p.src[k] = st->images[img].dev;
       p.src_tile_bytes[k] = st->images[img].tile_bytes;
-      p.src_smem_off[k] = off;
-      off += (st->images[img].tile_bytes + 127) & ~127u;
+      p.src_phase[k] = cur_phase;
+      p.src_smem_off[k] = off_phase[cur_phase];
+      off_phase[cur_phase] += (st->images[img].tile_bytes + 127) & ~127u;
+      off = std::max(off, off_phase[cur_phase]);
       return k;
     };
     // chunk list
@@ -538,13 +601,14 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     std::vector<WSrc> wsrc;
     uint32_t w_total = 0, w_stage = 0;
     auto add_chunks = [&](const std::vector<int>& imgs, int cin_total, int w_off_blob, int ktaps, int tap, int d, int acc,
-                          bool first_in_acc) {
+                          bool first_in_acc, int only = -1) {
       int ci = 0;
       bool first = first_in_acc;
       for (size_t si = 0; si < imgs.size(); ++si) {
         const TcImage& im = st->images[imgs[si]];
-        const int slot = add_src(imgs[si]);
         const int c_here = im.C;                       // channels of this source image (input image: 16, real 4)
+        if (only >= 0 && (int)si != only) { ci += (imgs[si] == 0) ? cfg.state_dim : c_here; continue; }
+        const int slot = add_src(imgs[si]);
         for (int c0 = 0; c0 < c_here; c0 += 32) {
           const int CK = std::min(32, c_here - c0);
           ChunkDesc cd{};
@@ -556,6 +620,7 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
           w_total += cd.w_bytes;
           w_stage = std::max(w_stage, cd.w_bytes);
           cd.d = d; cd.acc = acc; cd.first = first ? 1 : 0; cd.k16 = CK / 16;
+          cd.phase = cur_phase;
           first = false;
           chunks.push_back(cd);
           wsrc.push_back({net->blob + w_off_blob, cin_total, ktaps, tap, ci + c0, CK});
@@ -563,7 +628,19 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
         ci += (imgs[si] == 0) ? cfg.state_dim : c_here;
       }
     };
-    if (p.kind == TC_CONVBLOCK) {
+    if (streamed) {
+      bool first0 = true, first1 = true;
+      for (cur_phase = 0; cur_phase < (int)distinct.size(); ++cur_phase) {
+        const int img = distinct[cur_phase];
+        for (size_t k = 0; k < main_imgs.size(); ++k)
+          if (main_imgs[k] == img)
+            for (int tap = 0; tap < 5; ++tap) { add_chunks(main_imgs, op.cin, op.w, 5, tap, tap - 2, 0, first0, (int)k); first0 = false; }
+        if (res_conv)
+          for (size_t k = 0; k < res_imgs.size(); ++k)
+            if (res_imgs[k] == img) { add_chunks(res_imgs, op.res_cin, op.res_w, 1, 0, 0, 1, first1, (int)k); first1 = false; }
+      }
+      cur_phase = 0;
+    } else if (p.kind == TC_CONVBLOCK) {
       for (int tap = 0; tap < 5; ++tap) add_chunks(main_imgs, op.cin, op.w, 5, tap, tap - 2, 0, tap == 0);
       if (res_conv) add_chunks(res_imgs, op.res_cin, op.res_w, 1, 0, 0, 1, true);
     } else if (p.kind == TC_DOWN) {
@@ -580,8 +657,6 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     p.n_chunks = (int)chunks.size();
     p.w_stage_bytes = (w_stage + 127) & ~127u;
     p.smem_w_off = off;
-    const uint32_t scratch = (uint32_t)(5 * p.N + p.n_mt * 128 * 8 * 2 + 2 * ST * 8) * 4;
-    const uint32_t tail = ((scratch + 15) & ~15u) + 8 + 16 * MAX_W_STAGES + 8 + 16;
     // two CTAs per SM (one's epilogue under the other's MMAs) need <= ~112 KB each: shrink the weight ring if that helps
     p.w_stages = MAX_W_STAGES;
     if (off + MAX_W_STAGES * p.w_stage_bytes + tail > 114688u && off + 2 * p.w_stage_bytes + tail <= 114688u) p.w_stages = 2;
@@ -594,12 +669,14 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
     if (h.smem > 232448) return fail_free("tensor-core executor: layer does not fit in shared memory");
     // weights + chunk table to the device
     if (chunks.size() > (size_t)MAX_CHUNKS) return fail_free("tensor-core executor: too many weight chunks in one layer");
-    if (cudaMalloc(&h.w_dev, w_total) != cudaSuccess) return fail_free("out of memory (packed weights)");
-    for (size_t c = 0; c < chunks.size(); ++c) {
-      const WSrc& w = wsrc[c];
-      pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, op.cout, w.tap, w.ci0, w.CK, p.N,
-                                                reinterpret_cast<__half*>(h.w_dev + chunks[c].w_off));
-    }
+    if (cudaMalloc(&h.w_dev, (size_t)w_total * p.n_split) != cudaSuccess) return fail_free("out of memory (packed weights)");
+    p.w_split_bytes = w_total;
+    for (int sl = 0; sl < p.n_split; ++sl)
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        const WSrc& w = wsrc[c];
+        pack_wchunk_kernel<<<8, 256, 0, stream>>>(w.W, w.cin, w.ktaps, op.cout, w.tap, w.ci0, w.CK, p.N,
+                                                  reinterpret_cast<__half*>(h.w_dev + (size_t)sl * w_total + chunks[c].w_off), sl * p.N);
+      }
     for (size_t c = 0; c < chunks.size(); ++c) p.chunks[c] = chunks[c];
     p.cluster = TC_CLUSTER;
     p.wchunks = h.w_dev;
@@ -622,10 +699,22 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
 
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream) {
   (void)mode;
-  if (net->tc && net->tc->B != B) unet_tc_release(net);
-  if (!net->tc) {
-    int rc = build_tc(net, B, stream);
-    if (rc != MMDK_OK) return rc;
+  // one state (activation images + packed weights) per batch size: a planner warms up at B = 2 and then samples at B = K,
+  // CBS alternates single calls and batches -- none of that may rebuild (cudaFree / cudaMalloc / weight packing) every time
+  if (!net->tc || net->tc->B != B) {
+    auto it = net->tc_cache.find(B);
+    if (it != net->tc_cache.end()) {
+      net->tc = it->second;
+    } else {
+      if (net->tc_cache.size() >= 4) {   // bounded: drop everything that was cached and start over
+        MMDK_CUDA(cudaStreamSynchronize(stream));
+        unet_tc_release(net);
+      }
+      net->tc = nullptr;
+      int rc = build_tc(net, B, stream);
+      if (rc != MMDK_OK) return rc;
+      net->tc_cache[B] = net->tc;
+    }
   }
   TcState* st = net->tc;
   const auto& cfg = net->cfg;
@@ -639,12 +728,13 @@ int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float
     h.prm.cond = h.cond_off >= 0 ? cond_row + h.cond_off : nullptr;
     h.prm.eps = eps;
     int rc;
-    if (h.NV == 128 && h.N == 32) rc = launch_tc<128, 32>(h, stream);
-    else if (h.NV == 128 && h.N == 64) rc = launch_tc<128, 64>(h, stream);
-    else if (h.NV == 128 && h.N == 128) rc = launch_tc<128, 128>(h, stream);
-    else if (h.NV == 64 && h.N == 64) rc = launch_tc<64, 64>(h, stream);
-    else if (h.NV == 64 && h.N == 32) rc = launch_tc<64, 32>(h, stream);
-    else rc = launch_tc<64, 16>(h, stream);
+    if (h.NV == 128 && h.N == 32) rc = launch_tc<128, 32, 8>(h, stream);
+    else if (h.NV == 128 && h.N == 64) rc = launch_tc<128, 64, 8>(h, stream);
+    else if (h.NV == 128 && h.N == 128 && h.NG == 4) rc = launch_tc<128, 128, 4>(h, stream);
+    else if (h.NV == 128 && h.N == 128) rc = launch_tc<128, 128, 8>(h, stream);
+    else if (h.NV == 64 && h.N == 64) rc = launch_tc<64, 64, 8>(h, stream);
+    else if (h.NV == 64 && h.N == 32) rc = launch_tc<64, 32, 8>(h, stream);
+    else rc = launch_tc<64, 16, 8>(h, stream);
     if (rc != MMDK_OK) return rc;
   }
   return MMDK_OK;

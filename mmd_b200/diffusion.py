@@ -183,18 +183,21 @@ def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_step
     unet = model.model
     unet.ensure_time_table(max(t for t, _ in steps) + 1)
     def issue():
-        mode = _lib.UNET_MODES[unet.resolve_precision(model.unet_precision)]
+        mode = unet.native_mode(model.unet_precision)
         _lib.check(lib.mmdk_run_chain(unet.native(), mode, C.byref(env), C.byref(grp), C.byref(desc), H, _lib.ptr(x), _lib.ptr(eps),
                                       _lib.ptr(noise_steps), _lib.ptr(chain_steps), int(bool(use_graph)), _lib.stream_ptr()))
-    try:
-        issue()
-    except ValueError:
-        # unet_precision='auto' on a shape the tensor-core builder rejects: the exact native executor instead (the builder
-        # fails before the first launch of the chain, so x is untouched)
-        if (model.unet_precision or unet.unet_precision) != "auto" or unet.resolve_precision(model.unet_precision) == "fp32":
-            raise
-        unet._tc_rejected = True
-        issue()
+        return mode
+    while True:
+        mode = unet.native_mode(model.unet_precision)
+        try:
+            issue()
+            break
+        except ValueError:
+            # unet_precision='auto' on a shape a tensor-core builder rejects: the next native executor instead (a builder
+            # fails before the first launch of the chain, so x is untouched)
+            if (model.unet_precision or unet.unet_precision) != "auto" or mode == _lib.UNET_FP32:
+                raise
+            unet._note_rejection(mode)
     return keep
 
 

@@ -279,17 +279,28 @@ class MPD:
         return chain, t_sampling, t_post
 
 
-def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None) -> List[PlannerOutput]:
+def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None, rng: str = "sequential",
+               starts_goals: Optional[torch.Tensor] = None) -> List[PlannerOutput]:
     """Serves R planner calls (cbs.py:316-324 root loop; :390-430 the two children of an expansion) as ONE batched chain:
     planner r is group r of MultiRobotSampler(mode="independent"), i.e. its own hard conditions, constraint set and clip
     decision -- arithmetically the same as calling the planners one after the other, and the noise is drawn in the same order
     (per planner: x_T, then one frame per reverse step), so the results are bit-identical to sequential calls from the same
-    torch RNG state.  The planners must share the diffusion model, the environment and the guide weights."""
+    torch RNG state.  The planners must share the diffusion model, the environment and the guide weights.
+    MPDEnsemble planners (multi-tile, BASELINE config 5) are served the same way by _plan_batch_ensemble.
+    rng="batched" draws all noise in one call per tile instead (faster on the host, not the sequential calls' draw order).
+    starts_goals (optional, [R, 2, 2] on the device): the (start, goal) positions the caller plans for, checked against the
+    planners' stored states exactly as every planner's __call__ checks its arguments (mpd.py:308-315)."""
     from .sampler import MultiRobotSampler
     p0 = planners[0]
     R = len(planners)
     if constraints_l_l is None:
         constraints_l_l = [None] * R
+    if starts_goals is not None:
+        stored = torch.stack([torch.stack((p.start_state_pos, p.goal_state_pos)) for p in planners])
+        if not torch.allclose(starts_goals.to(stored), stored):
+            raise ValueError("A start or goal state is different from the one stored in its planner.")
+    if isinstance(p0, MPDEnsemble):
+        return _plan_batch_ensemble(planners, constraints_l_l, rng=rng)
     for p in planners:
         if p.model is not p0.model or p.num_samples != p0.num_samples or p.run_prior_only or p.run_prior_then_guidance:
             raise ValueError("plan_batch needs planners that share one model / n_samples and run the 'mmd' algorithm")
@@ -297,9 +308,12 @@ def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None) ->
     dev = p0.tensor_args['device']
     n_steps = p0.model.n_diffusion_steps + p0.n_diffusion_steps_without_noise
     noise = torch.empty(R, n_steps + 1, K, H, D, device=dev)
-    for r in range(R):   # the draw order of R sequential run_inference calls (diffusion.py run_inference)
-        noise[r, 0] = torch.randn(K, H, D, device=dev)
-        noise[r, 1:] = torch.stack([torch.randn(K, H, D, device=dev) for _ in range(n_steps)])
+    if rng == "batched":
+        noise.normal_()
+    else:
+        for r in range(R):   # the draw order of R sequential run_inference calls (diffusion.py run_inference)
+            noise[r, 0] = torch.randn(K, H, D, device=dev)
+            noise[r, 1:] = torch.stack([torch.randn(K, H, D, device=dev) for _ in range(n_steps)])
     cons, cons_objs = [], []
     for p, cl in zip(planners, constraints_l_l):
         ccs = [CostConstraint(p.robot, H, q_l=c.get_q_l(), traj_range_l=c.get_t_range_l(), radius_l=c.radius_l,
@@ -314,8 +328,11 @@ def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None) ->
                                                        n_diffusion_steps_without_noise=p0.n_diffusion_steps_without_noise)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    ev = _chain_events()
+    ev[0].record()
     _, chains = smp.sample([_hard_rows(p.hard_conds) for p in planners], K, noise=noise, mode="independent",
                            constraints_l=cons, return_chain=True)
+    ev[1].record()
     torch.cuda.synchronize()
     t_total = time.perf_counter() - t0
     outs = []
@@ -327,6 +344,19 @@ def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None) ->
 
 
 _batch_samplers = {}
+_chain_ev = []
+
+
+def _chain_events():
+    if not _chain_ev:
+        _chain_ev.extend([torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)])
+    return _chain_ev
+
+
+def last_batch_chain_ms():
+    """Device time (CUDA events on the launching stream) of the sampling chain of the last plan_batch call."""
+    torch.cuda.synchronize()
+    return _chain_ev[0].elapsed_time(_chain_ev[1])
 
 
 class DiffusionsEnsemble(nn.Module):
@@ -593,6 +623,10 @@ class MPDEnsemble:
             chains, _, _ = self.run_constrained_local_inference(cost_constraints_l, experience)
         torch.cuda.synchronize()
         t_total = time.perf_counter() - t0
+        return self._finish(chains, constraints_l, t_total)
+
+    def _finish(self, chains, constraints_l, t_total):
+        """mpd_ensemble.py:352-429: per tile unnormalise + classify, stitch the tiles in the global frame, statistics, smoothing."""
         per_tile = {}
         for m in self.models:
             iters, final, coll, coll_idxs, free, free_idxs = self.task.get_traj_unnormalized(m, self.datasets, chains[m])
@@ -696,6 +730,120 @@ class MPDEnsemble:
             for task_id in split:
                 self.guides[task_id].reset_extra_costs()
         return chains, t_sampling, t_post
+
+
+def _plan_batch_ensemble(planners: List["MPDEnsemble"], constraints_l_l, rng="sequential") -> List[PlannerOutput]:
+    """R MPDEnsemble planner calls (one per robot, cbs.py:316-324) as ONE batched multi-tile chain.
+
+    DiffusionsEnsemble.p_sample_loop (diffusion_ensemble.py:56-106) steps tile after tile inside every reverse step; here
+    every tile step runs for all R planners at once: planner r is group r of tile m's batch [R * K, H, D] (its own hard
+    conditions, split constraints and clip decision), and the cross conditioning runs per set of planners that share the tile
+    transforms (robots may traverse the tiles in different orders: inference_multi_agent.py:205-222).  Arithmetic and noise
+    draw order (per planner: x_T of every tile, then per step, per tile, one frame) are those of sequential calls, so from the
+    same torch RNG state the results are bit-identical to `[p(start, goal, constraints) for p in planners]`."""
+    from .diffusion import lower_for_step
+    p0 = planners[0]
+    R = len(planners)
+    tiles = list(p0.models.keys())
+    for p in planners:
+        if not isinstance(p, MPDEnsemble) or list(p.models.keys()) != tiles or any(p.models[m] is not p0.models[m] for m in tiles):
+            raise ValueError("plan_batch needs MPDEnsemble planners that share the per-tile diffusion models")
+        if (p.num_samples != p0.num_samples or p.run_prior_only or p.run_prior_then_guidance or p.n_guide_steps != p0.n_guide_steps
+                or p.t_start_guide != p0.t_start_guide or p.n_diffusion_steps_without_noise != p0.n_diffusion_steps_without_noise
+                or p.cross_conds != p0.cross_conds):
+            raise ValueError("plan_batch needs planners with one n_samples / guide schedule running the 'mmd' algorithm")
+    K, H = p0.num_samples, p0.n_support_points
+    D = p0.models[tiles[0]].state_dim
+    dev = p0.tensor_args['device']
+    T, n_extra = p0.model.n_diffusion_steps, p0.n_diffusion_steps_without_noise
+    n_steps = T + n_extra
+    B = R * K
+    noise = {m: torch.empty(n_steps + 1, B, H, D, device=dev) for m in tiles}
+    if rng == "sequential":
+        for r in range(R):   # the draw order of R sequential DiffusionsEnsemble.p_sample_loop calls
+            sl = slice(r * K, (r + 1) * K)
+            for m in tiles:
+                noise[m][0, sl] = torch.randn(K, H, D, device=dev)
+            for k in range(1, n_steps + 1):
+                for m in tiles:
+                    noise[m][k, sl] = torch.randn(K, H, D, device=dev)
+    elif rng == "batched":
+        for m in tiles:
+            noise[m].normal_()
+    else:
+        raise ValueError("rng must be 'sequential' or 'batched'")
+    # planners that share the tile transforms form one cross-conditioning call; keep the planners' order inside a set
+    sets = {}
+    for r, p in enumerate(planners):
+        sig = tuple(tuple(float(v) for v in p.transforms[m].reshape(-1).tolist()) for m in tiles)
+        sets.setdefault(sig, []).append(r)
+    order = [r for rs in sets.values() for r in rs]                # batch position -> planner index
+    pos = {r: i for i, r in enumerate(order)}
+    segs, a = [], 0
+    for rs in sets.values():
+        segs.append((a * K, (a + len(rs)) * K, planners[rs[0]].transforms))
+        a += len(rs)
+    if order != list(range(R)):
+        for m in tiles:
+            noise[m] = noise[m].view(n_steps + 1, R, K, H, D)[:, order].reshape(n_steps + 1, B, H, D).contiguous()
+    ordered = [planners[r] for r in order]
+    installed = []
+    try:
+        for r in order:
+            p, cl = planners[r], constraints_l_l[r]
+            ccs = [CostConstraint(p.robot, H, q_l=c.get_q_l(), traj_range_l=c.get_t_range_l(), radius_l=c.radius_l,
+                                  is_soft=c.is_soft, tensor_args=p.tensor_args) for c in (cl or [])]
+            installed.append((p, p._install_constraints(ccs)))
+        cons = {m: [p.guides[m]._own_constraints() for p in ordered] for m in tiles}
+        hcs = {m: [_hard_rows(p.hard_conds.get(m, {})) for p in ordered] for m in tiles}
+        x, eps, low_g, low_u = {}, {}, {}, {}
+        for m in tiles:
+            x[m] = noise[m][0].clone()
+            for g, hc in enumerate(hcs[m]):
+                for row, val in hc.items():
+                    x[m][g * K:(g + 1) * K, row, :] = val
+            eps[m] = torch.empty_like(x[m])
+            low_g[m] = lower_for_step(p0.guides[m], R, K, H, dev, hcs[m], cons[m])
+            low_u[m] = lower_for_step(None, R, K, H, dev, hcs[m], None)
+
+        def cross():
+            for lo, hi, tr in segs:
+                apply_cross_conditioning({m: x[m][lo:hi] for m in tiles}, p0.cross_conds, tr)
+
+        chains = {m: torch.empty(n_steps + 1, B, H, D, device=dev) for m in tiles}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev = _chain_events()
+        ev[0].record()
+        cross()
+        for m in tiles:
+            chains[m][0].copy_(x[m])
+        k = 1
+        for i in reversed(range(-n_extra, T)):
+            for m in tiles:
+                kw = p0.sample_kwargs[m]
+                guided = kw['guide'] is not None and i < kw['t_start_guide']
+                fn = kw.get('noise_std_extra_schedule_fn')
+                p0.models[m]._fused_step(x[m], hcs[m], i, kw['guide'] if guided else None, kw['n_guide_steps'], noise[m][k],
+                                         1.0 if fn is None else float(fn(i)), chain_slot=None, final_hard_cond=True,
+                                         lowered=low_g[m] if guided else low_u[m], eps_buf=eps[m], K=K,
+                                         constraints_per_group=cons[m])
+                cross()
+            for m in tiles:
+                chains[m][k].copy_(x[m])
+            k += 1
+        ev[1].record()
+        torch.cuda.synchronize()
+        t_total = time.perf_counter() - t0
+    finally:
+        for p, split in installed:
+            for task_id in split:
+                p.guides[task_id].reset_extra_costs()
+    outs = [None] * R
+    for r, p in enumerate(planners):
+        sl = slice(pos[r] * K, (pos[r] + 1) * K)
+        outs[r] = p._finish({m: chains[m][:, sl] for m in tiles}, constraints_l_l[r], t_total)
+    return outs
 
 
 class MultiPointConstraint:

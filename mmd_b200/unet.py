@@ -164,15 +164,94 @@ class TemporalUnet(nn.Module):
             return False
         return True
 
+    def _layer_program(self):
+        """(kind, [main source channel counts], [1x1 residual-conv source channel counts], cout, L) of every conv op in
+        execution order (temporal_unet.py:60-119,121-174; layers.py:326-358): the shapes the native builders see.  The
+        SECOND conv block of a ResidualTemporalBlock also evaluates the block's residual 1x1 conv (when cin != cout)."""
+        n = len(self.dim_mults)
+        dims = [self.state_dim] + [self.unet_input_dim * m for m in self.dim_mults]
+        L = [self.n_support_points >> i for i in range(n)]
+        ops = []
+
+        def rtb(srcs, cout, Li):
+            ops.append(("block", list(srcs), [], cout, Li))
+            ops.append(("block", [cout], list(srcs) if sum(srcs) != cout else [], cout, Li))
+
+        for i in range(n):
+            rtb([dims[i]], dims[i + 1], L[i])
+            rtb([dims[i + 1]], dims[i + 1], L[i])
+            if i < n - 1:
+                ops.append(("down", [dims[i + 1]], [], dims[i + 1], L[i]))
+        rtb([dims[n]], dims[n], L[n - 1])
+        rtb([dims[n]], dims[n], L[n - 1])
+        for j in range(n - 1, 0, -1):
+            rtb([dims[j + 1], dims[j + 1]], dims[j], L[j])
+            rtb([dims[j]], dims[j], L[j])
+            ops.append(("up", [dims[j]], [], dims[j], L[j]))
+        ops.append(("block", [dims[1]], [], dims[1], L[0]))
+        ops.append(("final", [dims[1]], [], self.state_dim, L[0]))
+        return ops
+
+    def tensor_core_layers_supported(self):
+        """Whether the per-layer tcgen05 executor (unet_tc.cu build_tc) covers this network shape.  Wider than the persistent
+        executor: 256-channel levels (dim_mults (1,2,4,8), the default of scripts/train_diffusion/train.py:35) run as two
+        128-channel slices, and ops whose source images do not fit shared memory together (the 512-channel concat blocks at
+        L = 8) stream them through one buffer, one image per input phase."""
+        if self.state_dim > 8 or self.self_attention:
+            return False
+        for kind, srcs, res_srcs, cout, Li in self._layer_program():
+            rows = 2 + 128 * ((7 * (Li + 2) + 127) // 128) + 2
+            n_mt = (rows - 4) // 128
+            N = 16 if kind == "final" else cout
+            split = 1
+            if kind == "block" and cout == 256:
+                N, split = 128, 2
+            if N not in (16, 32, 64, 128):
+                return False
+            NV = n_mt * N
+            if not ((NV == 128 and N in (32, 64, 128)) or (NV == 64 and N in (64, 32, 16))):
+                return False
+            if split > 1 and NV != 128:
+                return False
+            if kind == "block" and (cout < 8 or cout % 8 != 0):
+                return False
+            src_bytes = [((16 if c == self.state_dim else c) * rows * 4 + 127) // 128 * 128 for c in list(srcs) + list(res_srcs)]
+            scratch = (5 * N + n_mt * 128 * 8 * 2 + 2 * 7 * 8) * 4
+            fixed = 3 * 32 * N * 4 + (scratch + 15) // 16 * 16 + 80
+            if sum(src_bytes) + fixed > 232448:     # streamed: one source image per input phase
+                if kind != "block" or max(src_bytes) + fixed > 232448 or len(src_bytes) > 4:
+                    return False
+        return True
+
     def resolve_precision(self, precision=None):
-        """'auto' (default): the tensor-core executor ("f16x3": FP16 hi/lo split, ~3e-6 relative on eps) when the shape is
-        supported, else the exact fp32 CUDA-core executor.  Both are native sm_100a kernels."""
+        """'auto' (default): a tensor-core executor ("f16x3": FP16 hi/lo split, ~3e-6 relative on eps) when one covers the shape,
+        else the exact fp32 CUDA-core executor.  All are native sm_100a kernels; native_mode() picks the executor."""
         p = precision or self.unet_precision
-        if p == "auto" and getattr(self, "_tc_rejected", False):
-            return "fp32"   # the native builder refused this shape once (ValueError): exact executor from then on
+        if p == "auto" and getattr(self, "_tc_rejected", 0) >= 2:
+            return "fp32"   # both native tensor-core builders refused this shape (ValueError): exact executor from then on
         if p == "auto":
-            p = "f16x3" if self.tensor_core_supported() else "fp32"
+            p = "f16x3" if (self.tensor_core_supported() or self.tensor_core_layers_supported()) else "fp32"
         return p
+
+    def _note_rejection(self, mode):
+        """A native tensor-core builder refused the shape: 1 = persistent executor out, >= 2 = per-layer executor out too."""
+        r = getattr(self, "_tc_rejected", 0)
+        if mode == _lib.UNET_F16X3_LAYERS or not self.tensor_core_layers_supported():
+            r |= 2
+        if mode == _lib.UNET_F16X3:
+            r |= 1
+        self._tc_rejected = r
+
+    def native_mode(self, precision=None):
+        """mmdk_unet_forward mode for a precision: "f16x3" runs on the persistent whole-forward executor when it covers the
+        network shape, else on the per-layer tcgen05 executor (same numerics)."""
+        p = self.resolve_precision(precision)
+        if p in ("f16x3", "tc"):
+            rejected = getattr(self, "_tc_rejected", 0)
+            if (not self.tensor_core_supported() or (rejected & 1)) and self.tensor_core_layers_supported() and not (rejected & 2):
+                return _lib.UNET_F16X3_LAYERS
+            return _lib.UNET_F16X3
+        return _lib.UNET_MODES[p]
 
     # -- native handle ------------------------------------------------------------------------------------------
     def _invalidate(self):
@@ -265,14 +344,16 @@ class TemporalUnet(nn.Module):
         h = self.native()
         if out is None:
             out = torch.empty_like(x)
-        chosen = self.resolve_precision(precision)
-        try:
-            _lib.check(lib.mmdk_unet_forward(h, _lib.UNET_MODES[chosen], _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
-        except ValueError:
-            # 'auto' may only ever fall back to the exact NATIVE executor (never to a CPU / torch path), and only when the
-            # tensor-core builder rejects the network shape; an explicit precision request fails loudly
-            if (precision or self.unet_precision) != "auto" or chosen == "fp32":
-                raise
-            self._tc_rejected = True
-            _lib.check(lib.mmdk_unet_forward(h, _lib.UNET_FP32, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
+        while True:
+            mode = self.native_mode(precision)
+            try:
+                _lib.check(lib.mmdk_unet_forward(h, mode, _lib.ptr(x), x.shape[0], t, _lib.ptr(out), _lib.stream_ptr()))
+                break
+            except ValueError:
+                # 'auto' may only ever fall back to another NATIVE executor (persistent tcgen05 -> per-layer tcgen05 -> exact
+                # fp32; never a CPU / torch path), and only when a builder rejects the network shape; an explicit precision
+                # request fails loudly
+                if (precision or self.unet_precision) != "auto" or mode == _lib.UNET_FP32:
+                    raise
+                self._note_rejection(mode)
         return out

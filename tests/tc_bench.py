@@ -1,4 +1,6 @@
-"""UNet forward timing per executor (not a bench line: development tool).  usage: tc_bench.py [B] [modes...]"""
+"""UNet forward timing per executor (not a bench line: development tool).  usage: tc_bench.py [B] [modes...]
+MMD_DIM_MULTS=1,2,4,8 selects the 4-level network (per-layer tcgen05 executor vs the exact fp32 executor)."""
+import os
 import sys
 import time
 
@@ -11,8 +13,9 @@ from oracle import port  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 modes = sys.argv[2:] or ["f16x3_layers", "f16x3"]
 dev = torch.device("cuda:0")
-P = port.make_unet_params(seed=0)
-unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+DM = tuple(int(v) for v in os.environ.get("MMD_DIM_MULTS", "1,2,4").split(","))
+P = port.make_unet_params(seed=0, dim_mults=DM)
+unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=DM)
 unet.load_state_dict(P, strict=True)
 unet = unet.to(dev)
 x = torch.randn(B, 64, 4, device=dev)
@@ -34,4 +37,4 @@ for mode in modes:
     if ref is None:
         ref = out.clone()
     err = float((out - ref).norm() / ref.norm())
-    print(f"{mode:14s} B={B}: {ms:.3f} ms/forward  ({B * 36495360 / ms / 1e9:.1f} TFLOP/s algorithmic)  finite={fin}  rel diff vs first mode {err:.2e}")
+    print(f"dim_mults={DM} {mode:14s} B={B}: {ms:.3f} ms/forward  ({B * 36495360 / ms / 1e9:.1f} TFLOP/s algorithmic)  finite={fin}  rel diff vs first mode {err:.2e}")

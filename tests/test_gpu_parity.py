@@ -135,13 +135,40 @@ def test_unet_linear_attention(dev, B):
             assert e < bar
 
 
-def test_unet_dim_mults_option1(dev):
+@pytest.mark.parametrize("B", [3, 20, 300])
+def test_unet_dim_mults_option1(dev, B):
+    """dim_mults (1,2,4,8) (temporal_unet.py:17-20; the default of scripts/train_diffusion/train.py:35): exact fp32 executor,
+    and the per-layer tcgen05 executor -- 256-channel conv blocks at L = 8 as two 128-channel slices (4 GroupNorm groups each),
+    the 512-channel concat block streaming its two source images through shared memory in two phases.  Every layer tapped."""
+    import ctypes as C
+    from mmd_b200 import _lib
     o = build_oracle("EnvEmpty2D", T=25, dim_mults=(1, 2, 4, 8))
     p = build_product(dev, "EnvEmpty2D", T=25, P=o["P"], dim_mults=(1, 2, 4, 8))
-    x = torch.randn(3, 64, 4, generator=torch.Generator().manual_seed(3))
-    ref = port.unet_forward(o["P"], x, torch.full((3,), 4, dtype=torch.long))
-    out = p["unet"].forward_t(x.to(dev), 4)
-    assert rel_err(out, ref) < 2e-5
+    unet = p["unet"]
+    assert unet.resolve_precision("auto") == "f16x3" and unet.native_mode("auto") == _lib.UNET_F16X3_LAYERS
+    x = torch.randn(B, 64, 4, generator=torch.Generator().manual_seed(3))
+    for t in (4, 19):
+        taps = {}
+        ref = port.unet_forward(o["P"], x, torch.full((B,), t, dtype=torch.long), taps=taps)
+        if B <= 20:
+            assert rel_err(unet.forward_t(x.to(dev), t, precision="fp32"), ref) < 2e-5
+        out = unet.forward_t(x.to(dev), t, precision="f16x3")
+        h = unet.native()
+        worst = 0.0
+        for j, (name, act) in enumerate(taps["ops"]):            # every op but the final 1x1 conv (eps, checked below)
+            c, l = C.c_int(), C.c_int()
+            _lib.check(_lib.lib().mmdk_unet_debug_tap(h, j, None, C.byref(c), C.byref(l), None, _lib.stream_ptr()))
+            assert (c.value, l.value) == (act.shape[1], act.shape[2]), name
+            buf = torch.empty(B, c.value, l.value, device=dev)
+            _lib.check(_lib.lib().mmdk_unet_debug_tap(h, j, _lib.ptr(buf), C.byref(c), C.byref(l), None, _lib.stream_ptr()))
+            e = rel_err(buf, act)
+            worst = max(worst, e)
+            assert e < 5e-5, f"op {j} ({name}) rel_err {e:.3e}"
+        e = rel_err(out, ref)
+        print(f"unet (1,2,4,8) f16x3 (per-layer tcgen05) B={B} t={t}: eps rel_err={e:.3e}, worst layer {worst:.3e}")
+        assert e < 5e-5
+    # 'auto' picks the same executor, and a chain runs on it
+    assert torch.equal(unet.forward_t(x.to(dev), 19, precision="auto"), out)
 
 
 def test_cell_index_bit_exact(pair, dev):
@@ -697,6 +724,39 @@ def test_mpd_ensemble_planner(dev):
         e = _per_traj(chains_l[m][-1], ref_l[m][-1])
         print(f"MPDEnsemble local inference tile {m}: median={float(e.median()):.2e} max={float(e.max()):.2e}")
         assert float(e.median()) < 1e-4 and float(e.max()) < 2e-2
+
+
+def test_plan_batch_ensemble_equals_sequential_calls(dev):
+    """plan_batch on MPDEnsemble planners (BASELINE config 5: one multi-tile planner per robot, robots crossing the 1x2 tile
+    grid in both directions, inference_multi_agent.py:205-222) == the same planners called one after the other from the same
+    RNG state, bit for bit; one robot carries a soft constraint that is split over both tiles."""
+    import mmd_b200 as M
+    T, K = 25, 6
+    o = build_oracle("EnvEmptyNoWait2D", T=T, cutoff_margin=0.01)
+    unet = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    unet.load_state_dict(o["P"], strict=True)
+    model = M.GaussianDiffusionModel(model=unet, variance_schedule="exponential", n_diffusion_steps=T, predict_epsilon=True)
+    models = {0: model, 1: model}
+    fwd = {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}
+    bwd = {0: torch.tensor([2.0, 0.0]), 1: torch.tensor([0.0, 0.0])}
+    jobs = [(fwd, [-0.7, 0.1], [2.6, -0.2]), (bwd, [2.5, 0.4], [-0.6, 0.3]), (fwd, [-0.5, -0.6], [2.4, 0.5])]
+    planners = [M.MPDEnsemble(("EnvEmptyNoWait2D-RobotPlanarDisk",) * 2, tr, "mmd", torch.tensor(s), torch.tensor(g), n_samples=K,
+                              models=models, device="cuda:0") for tr, s, g in jobs]
+    cons = [None, None, [M.MultiPointConstraint([torch.tensor([-0.3, 0.0]).to(dev), torch.tensor([2.3, 0.1]).to(dev)],
+                                                [(10, 12), (84, 86)], [0.2, 0.2], is_soft=True)]]
+    torch.manual_seed(77)
+    seq = [planners[r](torch.tensor(jobs[r][1]).to(dev), torch.tensor(jobs[r][2]).to(dev), constraints_l=cons[r]) for r in range(3)]
+    torch.manual_seed(77)
+    bat = M.plan_batch(planners, cons)
+    for r in range(3):
+        assert seq[r].trajs_iters.shape == (T + 2, K, 128, 4)
+        assert torch.equal(seq[r].trajs_iters, bat[r].trajs_iters), f"robot {r}"
+        assert torch.equal(seq[r].trajs_final, bat[r].trajs_final)
+        assert torch.equal(seq[r].trajs_final_free_idxs, bat[r].trajs_final_free_idxs)
+    # the guides are left clean (constraints are per call)
+    assert all(len(g.extra_cost_l) == 0 for p in planners for g in p.guides.values())
+    fast = M.plan_batch(planners, cons, rng="batched")
+    assert fast[0].trajs_iters.shape == (T + 2, K, 128, 4) and bool(torch.isfinite(fast[0].trajs_iters).all())
 
 
 @pytest.mark.parametrize("n_peers", [31, 32, 63, 64, 65, 128, 256])

@@ -90,7 +90,21 @@ def test_lower_env_values():
 
 def test_executor_selection():
     assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4)).resolve_precision() == "f16x3"
-    assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4, 8)).resolve_precision() == "fp32"
+    from mmd_b200 import _lib
+    u3 = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4))
+    assert u3.native_mode() == _lib.UNET_F16X3 and u3.tensor_core_layers_supported()
+    # the 4-level default of scripts/train_diffusion/train.py:35 runs on the per-layer tcgen05 executor (256-channel layers as
+    # two 128-channel slices), same numerics class
+    u4 = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4, 8))
+    assert u4.resolve_precision() == "f16x3" and not u4.tensor_core_supported() and u4.native_mode() == _lib.UNET_F16X3_LAYERS
+    assert len(u4._layer_program()) == 4 * 4 + 3 + 4 + 3 * 5 + 2
+    # shapes no tensor-core tiling covers fall back to the exact native executor; a refused build is remembered
+    u5 = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=48, dim_mults=(1, 2))
+    assert u5.resolve_precision() == "fp32" and u5.native_mode() == _lib.UNET_FP32
+    u3._note_rejection(_lib.UNET_F16X3)
+    assert u3.native_mode() == _lib.UNET_F16X3_LAYERS and u3.resolve_precision() == "f16x3"
+    u3._note_rejection(_lib.UNET_F16X3_LAYERS)
+    assert u3.resolve_precision() == "fp32"
     assert M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4),
                           self_attention=True).resolve_precision() == "f16x3"   # LinearAttention runs on the tcgen05 executor too
     u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=(1, 2, 4), unet_precision="fp32")
