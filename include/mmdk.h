@@ -261,6 +261,45 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
                    const mmdk_chain_desc* chain, int H, float* x_dev, float* eps_dev, const float* noise_dev,
                    float* chain_out_dev, int use_graph, void* stream);
 
+/* The multi-tile reverse loop of DiffusionsEnsemble.p_sample_loop (mmd/models/diffusion_models/diffusion_ensemble.py:78-106)
+ * in ONE call: for every step i, for every tile m in order
+ *   mmdk_unet_forward(tile m, t_index[i]) -> mmdk_ddpm_step(tile m, scalars[i], noise frame i; the step applies the tile's
+ *   hard conditions itself) -> every cross condition (apply_cross_conditioning, sample_functions.py:17-31)
+ * and, after the last tile of the step, the chain frame i of every tile (the state AFTER all stitches, :103-105).
+ * A tile's batch is n_groups planner calls of K samples (mmdk_groups), so R multi-tile planner calls run as one chain; a cross
+ * condition applies to the batch rows [row_lo, row_hi) (planner calls that share the tile transforms).  use_graph != 0:
+ * captured once into a CUDA graph keyed on every pointer / scalar, replayed afterwards. */
+#define MMDK_MAX_TILES 8
+typedef struct {
+  const mmdk_unet* net;
+  int unet_mode;
+  const mmdk_guide_env* env;
+  const mmdk_groups* groups;
+  const mmdk_step_scalars* scalars;   /* [n_steps] (tile models may carry different schedules) */
+  float* x_dev;                       /* [B, H, D] in/out */
+  float* eps_dev;                     /* [B, H, D] scratch */
+  const float* noise_dev;             /* [n_steps, B, H, D] or NULL */
+  float* chain_out_dev;               /* [n_steps, B, H, D] or NULL */
+} mmdk_ensemble_tile;
+
+typedef struct {
+  int m1, m2;        /* tiles: x[m1][:, ind1, :] = min(x[m2][:, ind2, :] + rel, bnd); x[m2][:, ind2, :] = max(x[m1][:, ind1, :] - rel, -bnd) */
+  int ind1, ind2;
+  int row_lo, row_hi;
+  float rel[MMDK_STATE_DIM], bnd[MMDK_STATE_DIM];
+} mmdk_cross_cond;
+
+typedef struct {
+  int n_tiles;
+  const mmdk_ensemble_tile* tiles;
+  int n_steps;
+  const int* t_index;   /* [n_steps] */
+  int n_cross;
+  const mmdk_cross_cond* cross;
+} mmdk_ensemble_desc;
+
+int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ensemble, int H, int use_graph, void* stream);
+
 /* Publishes the representative sample of every group for the lock-step exchange: peers_out_dev[g] [H,2] =
  * unnormalise(x[g*K + rep_index])[:, :2] with the normaliser's clip rule applied to that group. */
 int mmdk_publish_peers(const mmdk_guide_env* env, int n_groups, int K, int H, int rep_index, const float* x_dev,

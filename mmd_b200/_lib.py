@@ -60,11 +60,27 @@ class ChainDesc(C.Structure):
                 ("exchange", C.POINTER(PeerExchange))]
 
 
+class EnsembleTile(C.Structure):
+    _fields_ = [("net", C.c_void_p), ("unet_mode", C.c_int), ("env", C.POINTER(GuideEnv)), ("groups", C.POINTER(Groups)),
+                ("scalars", C.POINTER(StepScalars)), ("x_dev", C.c_void_p), ("eps_dev", C.c_void_p), ("noise_dev", C.c_void_p),
+                ("chain_out_dev", C.c_void_p)]
+
+
+class CrossCond(C.Structure):
+    _fields_ = [("m1", C.c_int), ("m2", C.c_int), ("ind1", C.c_int), ("ind2", C.c_int), ("row_lo", C.c_int), ("row_hi", C.c_int),
+                ("rel", C.c_float * 4), ("bnd", C.c_float * 4)]
+
+
+class EnsembleDesc(C.Structure):
+    _fields_ = [("n_tiles", C.c_int), ("tiles", C.POINTER(EnsembleTile)), ("n_steps", C.c_int), ("t_index", C.POINTER(C.c_int)),
+                ("n_cross", C.c_int), ("cross", C.POINTER(CrossCond))]
+
+
 # every symbol declared in include/mmdk.h (checked by tests/test_abi.py)
 EXPORTS = [
     "mmdk_last_error", "mmdk_device_info", "mmdk_unet_create", "mmdk_unet_destroy", "mmdk_unet_forward",
     "mmdk_unet_cond_row", "mmdk_unet_debug_tap", "mmdk_unet_debug_timeline", "mmdk_unet_debug_stamps", "mmdk_unet_debug_keep_activations", "mmdk_debug_mma_calibrate", "mmdk_guide_grad", "mmdk_ddpm_step", "mmdk_ddpm_step_publish", "mmdk_wait_peers", "mmdk_p2p_alloc", "mmdk_p2p_free", "mmdk_p2p_export",
-    "mmdk_p2p_open", "mmdk_p2p_close", "mmdk_run_chain", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
+    "mmdk_p2p_open", "mmdk_p2p_close", "mmdk_run_chain", "mmdk_run_chain_ensemble", "mmdk_publish_peers", "mmdk_build_peer_hash", "mmdk_cross_condition",
     "mmdk_q_sample", "mmdk_cell_index", "mmdk_check_rr_collisions", "mmdk_classify_trajs", "mmdk_unnormalize", "mmdk_get_conflicts", "mmdk_smooth_trajs",
 ]
 
@@ -101,6 +117,7 @@ def load():
     lib.mmdk_guide_grad.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), i, vp, vp, vp, i, vp]
     lib.mmdk_ddpm_step.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp, vp]
     lib.mmdk_run_chain.argtypes = [vp, i, C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(ChainDesc), i, vp, vp, vp, vp, i, vp]
+    lib.mmdk_run_chain_ensemble.argtypes = [C.POINTER(EnsembleDesc), i, i, vp]
     lib.mmdk_publish_peers.argtypes = [C.POINTER(GuideEnv), i, i, i, i, vp, vp, vp]
     lib.mmdk_build_peer_hash.argtypes = [vp, vp, i, i, i, f, f, vp, vp, vp]
     lib.mmdk_ddpm_step_publish.argtypes = [C.POINTER(GuideEnv), C.POINTER(Groups), C.POINTER(StepScalars), i, vp, vp, vp, vp,

@@ -48,6 +48,51 @@ void push_bytes(GraphKey& k, const void* p, size_t n) {
 
 }  // namespace
 
+// Captures `issue` once per key into a CUDA graph (after `warm` ran everything that allocates / configures outside the
+// capture) and replays it; ordered after the caller's pending work on `s` and before its later work.
+template <class Warm, class Issue>
+static int run_graph(const GraphKey& key, Warm&& warm, Issue&& issue, cudaStream_t s) {
+  int dev = 0;
+  MMDK_CUDA(cudaGetDevice(&dev));
+  ChainCache& cc = cache_for_device(dev);
+  if (!cc.side) {
+    MMDK_CUDA(cudaStreamCreateWithFlags(&cc.side, cudaStreamNonBlocking));
+    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_in, cudaEventDisableTiming));
+    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_out, cudaEventDisableTiming));
+  }
+  // everything below runs on the side stream, ordered after the caller's pending work on `s`
+  MMDK_CUDA(cudaEventRecord(cc.ev_in, s));
+  MMDK_CUDA(cudaStreamWaitEvent(cc.side, cc.ev_in, 0));
+  auto it = cc.graphs.find(key);
+  if (it == cc.graphs.end()) {
+    int rc = warm(cc.side);
+    if (rc != MMDK_OK) return rc;
+    MMDK_CUDA(cudaStreamSynchronize(cc.side));
+    MMDK_CUDA(cudaStreamBeginCapture(cc.side, cudaStreamCaptureModeThreadLocal));
+    rc = issue(cc.side);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cc.side, &graph);
+    if (rc != MMDK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    MMDK_CUDA(ce);
+    GraphEntry ge;
+    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    MMDK_CUDA(ce);
+    if (cc.graphs.size() >= 8) {   // bounded: evict the least recently used graph
+      auto victim = cc.graphs.begin();
+      for (auto j = cc.graphs.begin(); j != cc.graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+      cudaGraphExecDestroy(victim->second.exec);
+      cc.graphs.erase(victim);
+    }
+    it = cc.graphs.emplace(key, ge).first;
+  }
+  it->second.last_use = ++cc.tick;
+  MMDK_CUDA(cudaGraphLaunch(it->second.exec, cc.side));
+  MMDK_CUDA(cudaEventRecord(cc.ev_out, cc.side));
+  MMDK_CUDA(cudaStreamWaitEvent(s, cc.ev_out, 0));
+  return MMDK_OK;
+}
+
 static int issue_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* env, const mmdk_groups* groups,
                        const mmdk_chain_desc* ch, int H, float* x, float* eps, const float* noise, float* chain_out,
                        cudaStream_t s) {
@@ -111,16 +156,9 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
   cudaStream_t s = (cudaStream_t)stream;
   if (!use_graph) return issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, s);
 
-  int dev = 0;
-  MMDK_CUDA(cudaGetDevice(&dev));
-  ChainCache& cc = cache_for_device(dev);
-  if (!cc.side) {
-    MMDK_CUDA(cudaStreamCreateWithFlags(&cc.side, cudaStreamNonBlocking));
-    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_in, cudaEventDisableTiming));
-    MMDK_CUDA(cudaEventCreateWithFlags(&cc.ev_out, cudaEventDisableTiming));
-  }
   // the graph bakes in every pointer and scalar: key on all of them
   GraphKey key;
+  key.words.push_back(1);   // kind: single-model chain
   key.words.push_back((uint64_t)(uintptr_t)net);
   key.words.push_back((uint64_t)unet_mode | ((uint64_t)H << 8) | ((uint64_t)chain->n_steps << 24) | ((uint64_t)chain->lockstep << 48) |
                       ((uint64_t)chain->rep_index << 49));
@@ -135,46 +173,101 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
   push_bytes(key, groups, sizeof(*groups));
   push_bytes(key, chain->scalars, sizeof(mmdk_step_scalars) * chain->n_steps);
   push_bytes(key, chain->t_index, sizeof(int) * chain->n_steps);
-
-  // everything below runs on the side stream, ordered after the caller's pending work on `s`
-  MMDK_CUDA(cudaEventRecord(cc.ev_in, s));
-  MMDK_CUDA(cudaStreamWaitEvent(cc.side, cc.ev_in, 0));
-  auto it = cc.graphs.find(key);
-  if (it == cc.graphs.end()) {
-    // warm everything that allocates or configures (executor state per batch size, function attributes) OUTSIDE the capture
+  auto warm = [&](cudaStream_t side) -> int {
+    // everything that allocates or configures (executor state per batch size, function attributes) OUTSIDE the capture
     const int B = groups->n_groups * groups->K;
-    int rc = mmdk_unet_forward(net, unet_mode, x_dev, B, chain->t_index[0], eps_dev, cc.side);
+    int rc = mmdk_unet_forward(net, unet_mode, x_dev, B, chain->t_index[0], eps_dev, side);
     if (rc != MMDK_OK) return rc;
-    {
-      mmdk_step_scalars dry = chain->scalars[0];
-      dry.n_guide_steps = 0; dry.do_posterior = 0; dry.add_noise = 0; dry.final_hard_conds = 0;   // x <- x: configures the launch only
-      rc = mmdk_ddpm_step(env, groups, &dry, H, x_dev, nullptr, nullptr, nullptr, cc.side);
+    mmdk_step_scalars dry = chain->scalars[0];
+    dry.n_guide_steps = 0; dry.do_posterior = 0; dry.add_noise = 0; dry.final_hard_conds = 0;   // x <- x: configures the launch only
+    return mmdk_ddpm_step(env, groups, &dry, H, x_dev, nullptr, nullptr, nullptr, side);
+  };
+  auto issue = [&](cudaStream_t side) -> int {
+    return issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, side);
+  };
+  return run_graph(key, warm, issue, s);
+}
+
+int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph, void* stream) {
+  if (!ens || ens->n_tiles < 1 || ens->n_tiles > MMDK_MAX_TILES || !ens->tiles) return fail(MMDK_EINVAL, "bad ensemble description");
+  if (ens->n_steps < 1 || !ens->t_index) return fail(MMDK_EINVAL, "empty chain description");
+  if (ens->n_cross > 0 && !ens->cross) return fail(MMDK_EINVAL, "null cross-condition list");
+  for (int m = 0; m < ens->n_tiles; ++m) {
+    const mmdk_ensemble_tile& t = ens->tiles[m];
+    if (!t.net || !t.env || !t.groups || !t.scalars || !t.x_dev || !t.eps_dev) return fail(MMDK_EINVAL, "null argument in a tile");
+    if (t.groups->peers_dev) return fail(MMDK_EINVAL, "lock-step peers are not part of the ensemble loop");
+  }
+  for (int c = 0; c < ens->n_cross; ++c) {
+    const mmdk_cross_cond& cc = ens->cross[c];
+    if (cc.m1 < 0 || cc.m1 >= ens->n_tiles || cc.m2 < 0 || cc.m2 >= ens->n_tiles || cc.row_lo < 0 || cc.row_hi < cc.row_lo)
+      return fail(MMDK_EINVAL, "bad cross condition");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  auto issue = [&](cudaStream_t q) -> int {
+    auto cross_all = [&]() -> int {
+      for (int c = 0; c < ens->n_cross; ++c) {
+        const mmdk_cross_cond& cc = ens->cross[c];
+        const size_t o = (size_t)cc.row_lo * H * MMDK_STATE_DIM;
+        int rc = mmdk_cross_condition(ens->tiles[cc.m1].x_dev + o, ens->tiles[cc.m2].x_dev + o, cc.row_hi - cc.row_lo, H, cc.ind1,
+                                      cc.ind2, cc.rel, cc.bnd, q);
+        if (rc != MMDK_OK) return rc;
+      }
+      return MMDK_OK;
+    };
+    for (int i = 0; i < ens->n_steps; ++i) {
+      for (int m = 0; m < ens->n_tiles; ++m) {
+        const mmdk_ensemble_tile& t = ens->tiles[m];
+        const size_t B = (size_t)t.groups->n_groups * t.groups->K;
+        const size_t frame = B * H * MMDK_STATE_DIM;
+        int rc = mmdk_unet_forward(t.net, t.unet_mode, t.x_dev, (int)B, ens->t_index[i], t.eps_dev, q);
+        if (rc != MMDK_OK) return rc;
+        rc = mmdk_ddpm_step(t.env, t.groups, &t.scalars[i], H, t.x_dev, t.eps_dev, t.noise_dev ? t.noise_dev + (size_t)i * frame : nullptr,
+                            nullptr, q);
+        if (rc != MMDK_OK) return rc;
+        rc = cross_all();   // diffusion_ensemble.py:99-101: after EVERY tile's step
+        if (rc != MMDK_OK) return rc;
+      }
+      for (int m = 0; m < ens->n_tiles; ++m) {   // the chain frame holds the step's state after all stitches (:103-105)
+        const mmdk_ensemble_tile& t = ens->tiles[m];
+        if (!t.chain_out_dev) continue;
+        const size_t frame = (size_t)t.groups->n_groups * t.groups->K * H * MMDK_STATE_DIM;
+        MMDK_CUDA(cudaMemcpyAsync(t.chain_out_dev + (size_t)i * frame, t.x_dev, frame * sizeof(float), cudaMemcpyDeviceToDevice, q));
+      }
+    }
+    return MMDK_OK;
+  };
+  if (!use_graph) return issue(s);
+  GraphKey key;
+  key.words.push_back(2);   // kind: ensemble chain
+  key.words.push_back(((uint64_t)H << 8) | ((uint64_t)ens->n_steps << 24) | ((uint64_t)ens->n_tiles << 48) | ((uint64_t)ens->n_cross << 52));
+  push_bytes(key, ens->t_index, sizeof(int) * ens->n_steps);
+  for (int m = 0; m < ens->n_tiles; ++m) {
+    const mmdk_ensemble_tile& t = ens->tiles[m];
+    key.words.push_back((uint64_t)(uintptr_t)t.net);
+    key.words.push_back((uint64_t)t.unet_mode);
+    key.words.push_back((uint64_t)(uintptr_t)t.x_dev);
+    key.words.push_back((uint64_t)(uintptr_t)t.eps_dev);
+    key.words.push_back((uint64_t)(uintptr_t)t.noise_dev);
+    key.words.push_back((uint64_t)(uintptr_t)t.chain_out_dev);
+    push_bytes(key, t.env, sizeof(*t.env));
+    push_bytes(key, t.groups, sizeof(*t.groups));
+    push_bytes(key, t.scalars, sizeof(mmdk_step_scalars) * ens->n_steps);
+  }
+  if (ens->n_cross) push_bytes(key, ens->cross, sizeof(mmdk_cross_cond) * ens->n_cross);
+  auto warm = [&](cudaStream_t side) -> int {
+    for (int m = 0; m < ens->n_tiles; ++m) {
+      const mmdk_ensemble_tile& t = ens->tiles[m];
+      const int B = t.groups->n_groups * t.groups->K;
+      int rc = mmdk_unet_forward(t.net, t.unet_mode, t.x_dev, B, ens->t_index[0], t.eps_dev, side);
+      if (rc != MMDK_OK) return rc;
+      mmdk_step_scalars dry = t.scalars[0];
+      dry.n_guide_steps = 0; dry.do_posterior = 0; dry.add_noise = 0; dry.final_hard_conds = 0;
+      rc = mmdk_ddpm_step(t.env, t.groups, &dry, H, t.x_dev, nullptr, nullptr, nullptr, side);
       if (rc != MMDK_OK) return rc;
     }
-    MMDK_CUDA(cudaStreamSynchronize(cc.side));
-    MMDK_CUDA(cudaStreamBeginCapture(cc.side, cudaStreamCaptureModeThreadLocal));
-    rc = issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, cc.side);
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(cc.side, &graph);
-    if (rc != MMDK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    MMDK_CUDA(ce);
-    GraphEntry ge;
-    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    MMDK_CUDA(ce);
-    if (cc.graphs.size() >= 8) {   // bounded: evict the least recently used graph
-      auto victim = cc.graphs.begin();
-      for (auto j = cc.graphs.begin(); j != cc.graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
-      cudaGraphExecDestroy(victim->second.exec);
-      cc.graphs.erase(victim);
-    }
-    it = cc.graphs.emplace(key, ge).first;
-  }
-  it->second.last_use = ++cc.tick;
-  MMDK_CUDA(cudaGraphLaunch(it->second.exec, cc.side));
-  MMDK_CUDA(cudaEventRecord(cc.ev_out, cc.side));
-  MMDK_CUDA(cudaStreamWaitEvent(s, cc.ev_out, 0));
-  return MMDK_OK;
+    return MMDK_OK;
+  };
+  return run_graph(key, warm, issue, s);
 }
 
 }  // extern "C"

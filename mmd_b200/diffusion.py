@@ -201,6 +201,65 @@ def run_chain_native(model, lowered, steps, x, eps, noise_steps=None, chain_step
     return keep
 
 
+def cross_cond_entries(cross_conds, transforms, D, row_lo, row_hi):
+    """[_lib.CrossCond] for the batch rows [row_lo, row_hi) from the reference's cross-condition dict and tile transforms
+    (sample_functions.py:17-31: rel = transforms[m2] - transforms[m1] padded to D, bnd = rel / |rel| with zeros -> 1e6)."""
+    out = []
+    for (m1, m2), (ind1, ind2) in cross_conds.items():
+        rel = (transforms[m2] - transforms[m1]).detach().to(torch.float32).cpu()
+        if D > rel.shape[0]:
+            rel = torch.cat([rel, torch.zeros(D - rel.shape[0])])
+        bnd = rel / torch.norm(rel, keepdim=True)
+        bnd[bnd == 0] = 1e6
+        cc = _lib.CrossCond()
+        cc.m1, cc.m2, cc.ind1, cc.ind2, cc.row_lo, cc.row_hi = int(m1), int(m2), int(ind1), int(ind2), int(row_lo), int(row_hi)
+        for d in range(4):
+            cc.rel[d], cc.bnd[d] = float(rel[d]), float(bnd[d])
+        out.append(cc)
+    return out
+
+
+def run_ensemble_chain_native(models, lowered, step_list, x, eps, noise_steps, chain_steps, cross_entries, use_graph=False):
+    """One mmdk_run_chain_ensemble call: the multi-tile reverse loop of DiffusionsEnsemble.p_sample_loop
+    (diffusion_ensemble.py:78-106).  models / lowered / x / eps / noise_steps / chain_steps: dicts keyed by tile (tiles must be
+    0..n-1 in order); step_list[m] = [(t_index, StepScalars)] per tile; noise_steps[m] / chain_steps[m]: contiguous
+    [n_steps, B, H, D] (or None); cross_entries: [_lib.CrossCond]."""
+    lib = _lib.lib()
+    tiles = list(models.keys())
+    assert tiles == list(range(len(tiles))), "ensemble tiles must be keyed 0..n-1"
+    n = len(step_list[tiles[0]])
+    t_arr = (C.c_int * n)(*[int(t) for t, _ in step_list[tiles[0]]])
+    tile_arr = (_lib.EnsembleTile * len(tiles))()
+    keep = [t_arr, tile_arr]
+    H = x[tiles[0]].shape[1]
+    for m in tiles:
+        assert [int(t) for t, _ in step_list[m]] == list(t_arr), "tile models must share the timestep sequence"
+        B, Hm, D = x[m].shape
+        sc_arr = (_lib.StepScalars * n)()
+        for i, (_, sc) in enumerate(step_list[m]):
+            sc_arr[i] = sc
+        unet = models[m].model
+        unet.ensure_time_table(max(t_arr) + 1)
+        env, grp, k = lowered[m]
+        keep += [sc_arr, k]
+        for nm, buf in (("noise", noise_steps), ("chain", chain_steps)):
+            if buf is not None and buf.get(m) is not None:
+                assert buf[m].is_contiguous() and buf[m].shape[0] >= n and tuple(buf[m].shape[1:]) == (B, Hm, D), nm
+        te = tile_arr[m]
+        te.net, te.unet_mode = unet.native(), unet.native_mode(models[m].unet_precision)
+        te.env, te.groups, te.scalars = C.pointer(env), C.pointer(grp), sc_arr
+        te.x_dev, te.eps_dev = x[m].data_ptr(), eps[m].data_ptr()
+        te.noise_dev = noise_steps[m].data_ptr() if noise_steps is not None and noise_steps.get(m) is not None else None
+        te.chain_out_dev = chain_steps[m].data_ptr() if chain_steps is not None and chain_steps.get(m) is not None else None
+    cross_arr = (_lib.CrossCond * max(1, len(cross_entries)))(*cross_entries)
+    desc = _lib.EnsembleDesc()
+    desc.n_tiles, desc.tiles, desc.n_steps, desc.t_index = len(tiles), tile_arr, n, t_arr
+    desc.n_cross, desc.cross = len(cross_entries), cross_arr
+    keep += [cross_arr, desc]
+    _lib.check(lib.mmdk_run_chain_ensemble(C.byref(desc), H, int(bool(use_graph)), _lib.stream_ptr()))
+    return keep
+
+
 class GaussianDiffusionModel(nn.Module):
     def __init__(self, model=None, variance_schedule='exponential', n_diffusion_steps=100, clip_denoised=True,
                  predict_epsilon=False, loss_type='l2', context_model=None, **kwargs):

@@ -17,7 +17,8 @@ import torch.nn as nn
 from . import envs as _envs
 from .costs import CostCollision, CostComposite, CostConstraint, CostGPTrajectory
 from .datasets import TrajectoryDataset
-from .diffusion import (GaussianDiffusionModel, apply_cross_conditioning, apply_hard_conditioning, ddpm_sample_fn,
+from .diffusion import (GaussianDiffusionModel, apply_cross_conditioning, apply_hard_conditioning, cross_cond_entries,
+                        ddpm_sample_fn, lower_for_step, run_ensemble_chain_native,
                         guide_gradient_steps, lower_for_step, _hard_rows)
 from .guides import GuideManagerTrajectoriesWithVelocity
 from .tasks import PlanningTask, RobotPlanarDisk
@@ -389,22 +390,41 @@ class DiffusionsEnsemble(nn.Module):
                 x[m] = (noise[m][0].to(dev).clone() if noise is not None else torch.randn(shape, device=dev)).contiguous()
             x[m] = apply_hard_conditioning(x[m], _hard_rows(hard_conds.setdefault(m, {})))
         x = apply_cross_conditioning(x, cross_conds, self.transforms)
-        chains = {m: [x[m].clone()] for m in self.models} if return_chain else None
-        k = 1
-        for i in reversed(range(-n_diffusion_steps_without_noise, n_diffusion_steps)):
-            t = torch.full((shape[0],), i, dtype=torch.long)
-            for m in self.models:
-                kw = dict(sample_kwargs['sample_kwargs'][m])
-                nz = noise[m][k].to(dev) if noise is not None else None
-                x[m], _ = sample_fn(self.models[m], x[m], hard_conds[m], None, t, noise=nz, **kw)
-                x[m] = apply_hard_conditioning(x[m], _hard_rows(hard_conds[m]))
-                x = apply_cross_conditioning(x, cross_conds, self.transforms)
-            if return_chain:
-                for m in self.models:
-                    chains[m].append(x[m].clone())
-            k += 1
+        # the whole multi-tile loop (:78-106) as ONE native call: per step, per tile, UNet forward -> fused posterior / guide /
+        # noise step (+ the tile's hard conditions) -> cross conditions; chain frames after the last tile of each step
+        if sample_fn is not ddpm_sample_fn:
+            raise NotImplementedError("only ddpm_sample_fn is lowered (mpd_ensemble.py:527)")
+        steps_i = list(reversed(range(-n_diffusion_steps_without_noise, n_diffusion_steps)))
+        n_steps, (B, _, D) = len(steps_i), shape
+        tiles = list(self.models.keys())
+        nz = {m: (noise[m][1:1 + n_steps].to(dev).to(torch.float32).contiguous() if noise is not None
+                  else torch.empty(n_steps, B, Hh, D, device=dev)) for m in tiles}
+        if noise is None:   # the reference's draw order: per step, per tile, one randn_like (:89-95)
+            for k in range(n_steps):
+                for m in tiles:
+                    nz[m][k] = torch.randn_like(x[m])
+        lowered, step_list, eps = {}, {}, {}
+        for m in tiles:
+            kw = dict(sample_kwargs['sample_kwargs'][m])
+            if kw.get('scale_grad_by_std'):
+                raise NotImplementedError("scale_grad_by_std=True is never used by the planners (sample_functions.py:45)")
+            if not self.models[m].clip_denoised:
+                raise RuntimeError("clip_denoised=False is rejected by the reference too (diffusion_model_base.py:157)")
+            guide, fn = kw.get('guide'), kw.get('noise_std_extra_schedule_fn')
+            n_g, t_sg = kw.get('n_guide_steps', 1), kw.get('t_start_guide', torch.inf)
+            hard_rows = _hard_rows(hard_conds[m])
+            lowered[m] = lower_for_step(guide, 1, B, Hh, dev, [hard_rows], [guide._own_constraints()] if guide is not None else None)
+            step_list[m] = [(max(i, 0), self.models[m].step_scalars(i, n_g if (guide is not None and i < t_sg) else 0,
+                                                                     1.0 if fn is None else float(fn(i)), True)) for i in steps_i]
+            eps[m] = torch.empty_like(x[m])
+        chain = {m: torch.empty(n_steps + 1, B, Hh, D, device=dev) for m in tiles} if return_chain else None
         if return_chain:
-            return x, {m: torch.stack(v, dim=1) for m, v in chains.items()}
+            for m in tiles:
+                chain[m][0].copy_(x[m])
+        run_ensemble_chain_native(self.models, lowered, step_list, x, eps, nz, {m: chain[m][1:] for m in tiles} if return_chain else None,
+                                  cross_cond_entries(cross_conds, self.transforms, D, 0, B))
+        if return_chain:
+            return x, {m: chain[m].transpose(0, 1) for m in tiles}   # [B, steps + 1, H, D] like torch.stack(chain, dim=1)
         return x
 
     @torch.no_grad()
@@ -741,7 +761,6 @@ def _plan_batch_ensemble(planners: List["MPDEnsemble"], constraints_l_l, rng="se
     transforms (robots may traverse the tiles in different orders: inference_multi_agent.py:205-222).  Arithmetic and noise
     draw order (per planner: x_T of every tile, then per step, per tile, one frame) are those of sequential calls, so from the
     same torch RNG state the results are bit-identical to `[p(start, goal, constraints) for p in planners]`."""
-    from .diffusion import lower_for_step
     p0 = planners[0]
     R = len(planners)
     tiles = list(p0.models.keys())
@@ -796,42 +815,33 @@ def _plan_batch_ensemble(planners: List["MPDEnsemble"], constraints_l_l, rng="se
             installed.append((p, p._install_constraints(ccs)))
         cons = {m: [p.guides[m]._own_constraints() for p in ordered] for m in tiles}
         hcs = {m: [_hard_rows(p.hard_conds.get(m, {})) for p in ordered] for m in tiles}
-        x, eps, low_g, low_u = {}, {}, {}, {}
+        x, eps, lowered, step_list = {}, {}, {}, {}
+        steps_i = list(reversed(range(-n_extra, T)))
         for m in tiles:
             x[m] = noise[m][0].clone()
             for g, hc in enumerate(hcs[m]):
                 for row, val in hc.items():
                     x[m][g * K:(g + 1) * K, row, :] = val
             eps[m] = torch.empty_like(x[m])
-            low_g[m] = lower_for_step(p0.guides[m], R, K, H, dev, hcs[m], cons[m])
-            low_u[m] = lower_for_step(None, R, K, H, dev, hcs[m], None)
-
-        def cross():
-            for lo, hi, tr in segs:
-                apply_cross_conditioning({m: x[m][lo:hi] for m in tiles}, p0.cross_conds, tr)
-
+            kw = p0.sample_kwargs[m]
+            guide, fn = kw['guide'], kw.get('noise_std_extra_schedule_fn')
+            lowered[m] = lower_for_step(guide, R, K, H, dev, hcs[m], cons[m] if guide is not None else None)
+            step_list[m] = [(max(i, 0), p0.models[m].step_scalars(i, kw['n_guide_steps'] if (guide is not None and i < kw['t_start_guide']) else 0,
+                                                                  1.0 if fn is None else float(fn(i)), True)) for i in steps_i]
+        cross_entries = []
+        for lo, hi, tr in segs:
+            apply_cross_conditioning({m: x[m][lo:hi] for m in tiles}, p0.cross_conds, tr)
+            cross_entries += cross_cond_entries(p0.cross_conds, tr, D, lo, hi)
         chains = {m: torch.empty(n_steps + 1, B, H, D, device=dev) for m in tiles}
+        for m in tiles:
+            chains[m][0].copy_(x[m])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ev = _chain_events()
         ev[0].record()
-        cross()
-        for m in tiles:
-            chains[m][0].copy_(x[m])
-        k = 1
-        for i in reversed(range(-n_extra, T)):
-            for m in tiles:
-                kw = p0.sample_kwargs[m]
-                guided = kw['guide'] is not None and i < kw['t_start_guide']
-                fn = kw.get('noise_std_extra_schedule_fn')
-                p0.models[m]._fused_step(x[m], hcs[m], i, kw['guide'] if guided else None, kw['n_guide_steps'], noise[m][k],
-                                         1.0 if fn is None else float(fn(i)), chain_slot=None, final_hard_cond=True,
-                                         lowered=low_g[m] if guided else low_u[m], eps_buf=eps[m], K=K,
-                                         constraints_per_group=cons[m])
-                cross()
-            for m in tiles:
-                chains[m][k].copy_(x[m])
-            k += 1
+        # the whole multi-tile chain of all planner calls: one native call (mmdk_run_chain_ensemble)
+        run_ensemble_chain_native(p0.models, lowered, step_list, x, eps, {m: noise[m][1:] for m in tiles},
+                                  {m: chains[m][1:] for m in tiles}, cross_entries)
         ev[1].record()
         torch.cuda.synchronize()
         t_total = time.perf_counter() - t0
