@@ -444,6 +444,7 @@ __device__ __forceinline__ void epi_convblock(const FOp* __restrict__ op, const 
 }
 
 // Down / up resampling convs and the final 1x1 conv: bias only, no normalisation (layers.py:261-276, temporal_unet.py:116-119)
+template <bool ATTN>
 __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiCtx& c, uint32_t bar_acc_empty, float* eps) {
   const int N = op->N, NMT = op->n_mt, L = op->L, Pp = op->P;
   const uint32_t lane_base = c.tmem + ((uint32_t)(c.q4 * 32) << 16);
@@ -474,14 +475,14 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
     for (int region = 0; region < n_regions; ++region) {
 #pragma unroll 1
       for (int i = 0; i < NMT; ++i) {
-        const int q = ((op->kind == TC_ATTN_OUT) ? op->q_base : 0) + 128 * i + c.row;
+        const int q = ((ATTN && op->kind == TC_ATTN_OUT) ? op->q_base : 0) + 128 * i + c.row;
         const int si = (int)(((uint32_t)q * pinv) >> 16), pi = q - si * Pp;
         bool ok = (si < c.st) && (pi < L) && (c.tile * c.st + si < c.B);
         int ro;
         if (op->kind == TC_DOWN) {   // stride-2 conv evaluated at every position; keep the even ones
           ok = ok && ((pi & 1) == 0);
           ro = 2 + si * Po + (pi >> 1);
-        } else if (op->kind == TC_ATTN_OUT) {   // to_out 1x1 conv at the same resolution (+ bias + residual x below)
+        } else if (ATTN && op->kind == TC_ATTN_OUT) {   // to_out 1x1 conv at the same resolution (+ bias + residual x below)
           ro = 2 + q;
         } else {                      // transposed conv: region 0 -> output 2p, region 1 -> 2p + 1
           ro = 2 + si * Po + 2 * pi + region;
@@ -496,7 +497,7 @@ __device__ __forceinline__ void epi_plain(const FOp* __restrict__ op, const EpiC
           if (ok) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] += c.p_bias[cbase + e];
-            if (op->kind == TC_ATTN_OUT && op->res_id != nullptr) {   // Residual(...): + x
+            if (ATTN && op->kind == TC_ATTN_OUT && op->res_id != nullptr) {   // Residual(...): + x
               const uint8_t* rp = op->res_id + (size_t)c.img * op->res_id_tile_bytes + ((size_t)(cbase / 8) * op->res_id_rows + 2 + q) * 16;
               const uint4 rh = ld_cg_u4(rp), rl = ld_cg_u4(rp + (size_t)(op->res_id_C / 8) * op->res_id_rows * 16);
               add8(rh, rl, y);
@@ -629,6 +630,9 @@ __device__ __forceinline__ void epi_attn_core(const FOp* __restrict__ op, const 
   }
 }
 
+// ATTN: the LinearAttention epilogues are compiled in (a separate instantiation keeps them out of the register allocation and
+// the instruction stream of the attention-free networks every shipped config uses)
+template <bool ATTN>
 __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_constant__ FParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -881,12 +885,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
           case FV_1_32: epi_convblock<1, 32>(op, c, bae); break;
           default: epi_convblock<1, 64>(op, c, bae); break;
         }
-      } else if (op->kind == TC_ATTN_QKV) {
-        epi_attn_qkv(op, c, bae);
-      } else if (op->kind == TC_ATTN_CORE) {
-        epi_attn_core(op, c, bae);
+      } else if (ATTN && op->kind == TC_ATTN_QKV) {
+        if constexpr (ATTN) epi_attn_qkv(op, c, bae);
+      } else if (ATTN && op->kind == TC_ATTN_CORE) {
+        if constexpr (ATTN) epi_attn_core(op, c, bae);
       } else {
-        epi_plain(op, c, bae, P.eps);
+        epi_plain<ATTN>(op, c, bae, P.eps);
       }
       // output image visible to the async proxy (the input producer's bulk copies / the next op's MMAs) before the arrival
       fence_proxy_async_global();
@@ -1338,7 +1342,8 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
     if (!configured[dev]) {
       int max_optin = 0;
       MMDK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      MMDK_CUDA(cudaFuncSetAttribute(unet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+      MMDK_CUDA(cudaFuncSetAttribute(unet_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+      MMDK_CUDA(cudaFuncSetAttribute(unet_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
       configured[dev] = true;
     }
   }
@@ -1358,7 +1363,8 @@ int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, 
     P.stamp = net->stamps + (size_t)(net->stamp_next++ % net->stamp_slots) * net->stamp_ctas * 2;
   }
   { const char* e = getenv("MMDK_FUSED_DEBUG"); P.dbg_flags = e ? atoi(e) : 0; }
-  unet_fused_kernel<<<st->grid, F_THREADS, st->smem, stream>>>(P);
+  if (cfg.self_attention) unet_fused_kernel<true><<<st->grid, F_THREADS, st->smem, stream>>>(P);
+  else unet_fused_kernel<false><<<st->grid, F_THREADS, st->smem, stream>>>(P);
   return check_cuda(cudaGetLastError(), "unet_fused_kernel launch");
 }
 

@@ -312,9 +312,9 @@ def plan_batch(planners: List["MPD"], constraints_l_l: Optional[List] = None, rn
     if rng == "batched":
         noise.normal_()
     else:
-        for r in range(R):   # the draw order of R sequential run_inference calls (diffusion.py run_inference)
-            noise[r, 0] = torch.randn(K, H, D, device=dev)
-            noise[r, 1:] = torch.stack([torch.randn(K, H, D, device=dev) for _ in range(n_steps)])
+        for r in range(R):   # the draw order of R sequential run_inference calls (diffusion.py run_inference): x_T, then one
+            for k in range(n_steps + 1):   # frame per step -- drawn straight into the batch buffer (same Philox offsets, no copies)
+                torch.randn((K, H, D), out=noise[r, k])
     cons, cons_objs = [], []
     for p, cl in zip(planners, constraints_l_l):
         ccs = [CostConstraint(p.robot, H, q_l=c.get_q_l(), traj_range_l=c.get_t_range_l(), radius_l=c.radius_l,
@@ -782,10 +782,10 @@ def _plan_batch_ensemble(planners: List["MPDEnsemble"], constraints_l_l, rng="se
         for r in range(R):   # the draw order of R sequential DiffusionsEnsemble.p_sample_loop calls
             sl = slice(r * K, (r + 1) * K)
             for m in tiles:
-                noise[m][0, sl] = torch.randn(K, H, D, device=dev)
+                torch.randn((K, H, D), out=noise[m][0, sl])
             for k in range(1, n_steps + 1):
                 for m in tiles:
-                    noise[m][k, sl] = torch.randn(K, H, D, device=dev)
+                    torch.randn((K, H, D), out=noise[m][k, sl])
     elif rng == "batched":
         for m in tiles:
             noise[m].normal_()
