@@ -171,6 +171,35 @@ def test_unet_dim_mults_option1(dev, B):
     assert torch.equal(unet.forward_t(x.to(dev), 19, precision="auto"), out)
 
 
+def test_dim_mults_option1_chain(dev):
+    """The 4-level network through the whole reverse chain on its tensor-core (per-layer tcgen05) executor: run_inference
+    (native chain, issued directly) against the oracle with the GP term off, and the same planner call through the
+    graph-captured batched sampler (MultiRobotSampler independent mode: PDL launches inside a CUDA graph) == run_inference
+    bit for bit."""
+    import mmd_b200 as M
+    T, K = 25, 8
+    o = build_oracle("EnvHighways2D", T=T, dim_mults=(1, 2, 4, 8), w_smooth=0.0)
+    p = build_product(dev, "EnvHighways2D", T=T, P=o["P"], dim_mults=(1, 2, 4, 8), w_smooth=0.0, precision="auto")
+    assert p["unet"].native_mode("auto") == M._lib.UNET_F16X3_LAYERS
+    noise = torch.randn(T + 2, K, 64, 4, generator=torch.Generator().manual_seed(18))
+    hc = port.hard_conds_from_start_goal(torch.tensor([-0.8, 0.0]), torch.tensor([0.8, 0.1]), o["norm"])
+    ref = port.run_inference(o["model"], hc, K, noise, guide=o["guide"])
+    kw = dict(n_samples=K, horizon=64, return_chain=True, sample_fn=M.ddpm_sample_fn, n_guide_steps=20,
+              t_start_guide=math.ceil(0.5 * T), noise_std_extra_schedule_fn=lambda x: 0.5, n_diffusion_steps_without_noise=1)
+    hcd = {k: v.to(dev) for k, v in hc.items()}
+    chain = p["model"].run_inference(None, hcd, guide=p["guide"], noise=noise.to(dev), **kw)
+    fin = _per_traj(chain[-1], ref[-1])
+    print(f"chain (1,2,4,8) f16x3 K={K} T={T} w_smooth=0: final rel L2 median={float(fin.median()):.2e} max={float(fin.max()):.2e}")
+    assert torch.isfinite(chain).all()
+    assert float(fin.median()) < 1e-4 and float(fin.quantile(0.9)) < 1e-3 and float(fin.max()) < 2e-2
+    smp = M.MultiRobotSampler(p["model"], p["guide"], n_guide_steps=20, t_start_guide=math.ceil(0.5 * T), noise_std=0.5,
+                              n_diffusion_steps_without_noise=1)
+    for _ in range(2):   # capture, then replay
+        out, ch = smp.sample([hcd], K, noise=noise.to(dev)[None],
+                             mode="independent", return_chain=True)
+        assert torch.equal(ch[0], chain)
+
+
 def test_cell_index_bit_exact(pair, dev):
     import ctypes as C
     from mmd_b200 import _lib
