@@ -177,3 +177,23 @@ def test_soft_constraints_from_paths_equals_the_reference_loops():
         a, b = ConstraintSet([c_vec], [2e-2], 64, torch.device("cpu")), ConstraintSet([c_ref], [2e-2], 64, torch.device("cpu"))
         assert torch.equal(a.bucket_ptr, b.bucket_ptr) and torch.equal(a.cons, b.cons)
     assert soft_constraints_from_paths([], [], 0) == []
+
+
+def test_cross_cond_entries_match_the_reference_vectors():
+    """mmdk_cross_cond entries (include/mmdk.h) carry the rel / bnd vectors of apply_cross_conditioning (sample_functions.py:17-31)
+    for both traversal directions of a 1x2 tile grid, restricted to a batch-row range."""
+    from mmd_b200.diffusion import cross_cond_entries
+    for tr in ({0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}, {0: torch.tensor([2.0, 0.0]), 1: torch.tensor([0.0, 0.0])},
+               {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([0.0, -2.0])}):
+        (cc,) = cross_cond_entries({(0, 1): (63, 0)}, tr, 4, 128, 192)
+        rel = torch.cat([tr[1] - tr[0], torch.zeros(2)])
+        bnd = rel / torch.norm(rel, keepdim=True)
+        bnd[bnd == 0] = 1e6
+        assert (cc.m1, cc.m2, cc.ind1, cc.ind2, cc.row_lo, cc.row_hi) == (0, 1, 63, 0, 128, 192)
+        assert list(cc.rel) == rel.tolist() and list(cc.bnd) == [float(torch.tensor(v, dtype=torch.float32)) for v in bnd.tolist()]
+        # the oracle's stitch with these vectors == the reference expression
+        x = {0: torch.randn(3, 64, 4), 1: torch.randn(3, 64, 4)}
+        y = port.apply_cross_conditioning({m: v.clone() for m, v in x.items()}, {(0, 1): (63, 0)}, tr)
+        r, b = torch.tensor(list(cc.rel)), torch.tensor(list(cc.bnd))
+        a1 = torch.min(x[1][:, 0, :] + r, b)
+        assert torch.equal(y[0][:, 63, :], a1) and torch.equal(y[1][:, 0, :], torch.max(a1 - r, -b))
