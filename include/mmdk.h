@@ -241,7 +241,9 @@ int mmdk_p2p_close(void* dev);
  *   [lockstep, guided steps only: mmdk_publish_peers -> mmdk_build_peer_hash]  ->  mmdk_unet_forward(t_index[i])  ->
  *   mmdk_ddpm_step(scalars[i], noise frame i, chain frame i)
  * issued natively on `stream`; with use_graph != 0 the sequence is captured once into a CUDA graph (keyed on every pointer
- * and scalar it bakes in) and replayed, so a chain costs one graph launch.  noise_dev [n_steps, B, H, D] step-major (NULL:
+ * and scalar it bakes in, plus process-unique ids of the UNet handle and of its executor state for this batch size: a
+ * handle re-created after a weight reload, or a state evicted from the bounded per-batch-size cache and rebuilt, never
+ * matches an old graph) and replayed, so a chain costs one graph launch.  noise_dev [n_steps, B, H, D] step-major (NULL:
  * no noise added), chain_out_dev [n_steps, B, H, D] (NULL: keep only x_dev), eps_dev [B, H, D] scratch.  Lock-step with
  * the fleet sharded over several processes needs an exchange between publication and hash build: that path stays in the
  * host loop (mmd_b200/sampler.py); peers_local_dev = the rows of groups->peers_dev that belong to this call's groups. */

@@ -1,4 +1,5 @@
 // C ABI glue of libmmdk: error reporting, device probe, mmdk_unet_* entry points (see include/mmdk.h).
+#include <atomic>
 #include <string>
 
 #include "common.cuh"
@@ -17,6 +18,17 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return MMDK_OK;
   g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
   return MMDK_ECUDA;
+}
+
+uint64_t next_uid() {
+  static std::atomic<uint64_t> counter{0};
+  return ++counter;
+}
+
+uint64_t unet_state_uid(const UnetImpl* net, int mode, int B) {
+  if (mode == MMDK_UNET_F16X3) return unet_fused_state_uid(net, B);
+  if (mode == MMDK_UNET_F16X3_LAYERS) return unet_tc_state_uid(net, B);
+  return net->uid;
 }
 
 __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
@@ -55,9 +67,14 @@ int mmdk_unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* con
   UnetImpl* impl = nullptr;
   int rc = unet_create(cfg, n_tensors, names, tensors_dev, numels, (cudaStream_t)stream, &impl);
   if (rc != MMDK_OK) return rc;
+  impl->uid = next_uid();
   *out = new mmdk_unet{impl};
   return MMDK_OK;
 }
+
+/* internal (chain.cu): ids that make a captured graph's key unique to the handle and executor state it baked in */
+uint64_t mmdk_internal_unet_uid(const mmdk_unet* net) { return net ? net->impl->uid : 0; }
+uint64_t mmdk_internal_state_uid(const mmdk_unet* net, int mode, int B) { return net ? unet_state_uid(net->impl, mode, B) : 0; }
 
 void mmdk_unet_destroy(mmdk_unet* net) {
   if (!net) return;

@@ -10,6 +10,10 @@
 
 #include "common.cuh"
 
+struct mmdk_unet;
+extern "C" uint64_t mmdk_internal_unet_uid(const mmdk_unet* net);                      // api.cu
+extern "C" uint64_t mmdk_internal_state_uid(const mmdk_unet* net, int mode, int B);   // api.cu
+
 namespace mmdk {
 
 namespace {
@@ -157,8 +161,17 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
   if (!use_graph) return issue_chain(net, unet_mode, env, groups, chain, H, x_dev, eps_dev, noise_dev, chain_out_dev, s);
 
   // the graph bakes in every pointer and scalar: key on all of them
+  // the executor state of this batch size must exist before the key is built: its id is part of the key (a state that was
+  // evicted and rebuilt, or a handle re-created at the same address after a weight reload, must never match an old graph)
+  const int B_all = groups->n_groups * groups->K;
+  if (mmdk_internal_state_uid(net, unet_mode, B_all) == 0) {
+    int rc = mmdk_unet_forward(net, unet_mode, x_dev, B_all, chain->t_index[0], eps_dev, s);   // eps is scratch: harmless
+    if (rc != MMDK_OK) return rc;
+  }
   GraphKey key;
   key.words.push_back(1);   // kind: single-model chain
+  key.words.push_back(mmdk_internal_unet_uid(net));
+  key.words.push_back(mmdk_internal_state_uid(net, unet_mode, B_all));
   key.words.push_back((uint64_t)(uintptr_t)net);
   key.words.push_back((uint64_t)unet_mode | ((uint64_t)H << 8) | ((uint64_t)chain->n_steps << 24) | ((uint64_t)chain->lockstep << 48) |
                       ((uint64_t)chain->rep_index << 49));
@@ -237,6 +250,14 @@ int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph,
     return MMDK_OK;
   };
   if (!use_graph) return issue(s);
+  for (int m = 0; m < ens->n_tiles; ++m) {   // executor states first: their ids are part of the key (see mmdk_run_chain)
+    const mmdk_ensemble_tile& t = ens->tiles[m];
+    const int B = t.groups->n_groups * t.groups->K;
+    if (mmdk_internal_state_uid(t.net, t.unet_mode, B) == 0) {
+      int rc = mmdk_unet_forward(t.net, t.unet_mode, t.x_dev, B, ens->t_index[0], t.eps_dev, s);
+      if (rc != MMDK_OK) return rc;
+    }
+  }
   GraphKey key;
   key.words.push_back(2);   // kind: ensemble chain
   key.words.push_back(((uint64_t)H << 8) | ((uint64_t)ens->n_steps << 24) | ((uint64_t)ens->n_tiles << 48) | ((uint64_t)ens->n_cross << 52));
@@ -244,6 +265,8 @@ int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph,
   for (int m = 0; m < ens->n_tiles; ++m) {
     const mmdk_ensemble_tile& t = ens->tiles[m];
     key.words.push_back((uint64_t)(uintptr_t)t.net);
+    key.words.push_back(mmdk_internal_unet_uid(t.net));
+    key.words.push_back(mmdk_internal_state_uid(t.net, t.unet_mode, t.groups->n_groups * t.groups->K));
     key.words.push_back((uint64_t)t.unet_mode);
     key.words.push_back((uint64_t)(uintptr_t)t.x_dev);
     key.words.push_back((uint64_t)(uintptr_t)t.eps_dev);

@@ -9,7 +9,13 @@ namespace mmdk {
 struct TcState;     // per-layer tcgen05 executor state (unet_tc.cu)
 struct FusedState;  // persistent whole-forward tcgen05 executor state (unet_fused.cu)
 
+// Process-wide unique ids: a captured CUDA graph (chain.cu) bakes in the device pointers of a network handle AND of the executor
+// state (activation images, packed weights) of one batch size; both can be destroyed and re-created -- possibly at the same host
+// address -- so graph keys carry these ids instead of trusting pointers.
+uint64_t next_uid();
+
 struct UnetImpl {
+  uint64_t uid = 0;
   mmdk_unet_config cfg{};
   std::vector<Op> ops;       // host copy of the layer program
   Op* ops_dev = nullptr;
@@ -35,6 +41,10 @@ struct UnetImpl {
 int unet_create(const mmdk_unet_config* cfg, int n_tensors, const char* const* names, const float* const* tensors,
                 const int64_t* numels, cudaStream_t stream, UnetImpl** out);
 void unet_destroy(UnetImpl* net);
+// id of the executor state that mode `mode` would use for batch size B right now (0: not built yet; fp32: the handle's id)
+uint64_t unet_state_uid(const UnetImpl* net, int mode, int B);
+uint64_t unet_fused_state_uid(const UnetImpl* net, int B);
+uint64_t unet_tc_state_uid(const UnetImpl* net, int B);
 int unet_forward_ffma(const UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream);
 
 // persistent whole-forward tcgen05 executor (unet_fused.cu)

@@ -921,6 +921,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) unet_fused_kernel(const __grid_c
 // host
 // ------------------------------------------------------------------------------------------------------------------
 struct FusedState {
+  uint64_t uid = 0;
   int B = 0, n_tiles = 0, grid = 0, by_slot = 0, st = ST;
   bool keep_all = false;           // every activation image also goes to global memory (debug taps)
   std::vector<TcImage> images;     // [0] = packed network input, [1 + j] = output of op j
@@ -954,6 +955,7 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   MMDK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   MMDK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   auto* st = new FusedState();
+  st->uid = next_uid();
   st->B = B;
   // samples per tile.  Measured kernel durations on B200 (tests/tc_stamps.py): a lone tile's 30-op chain costs 196 us with 1
   // sample, 204 us with 3, 255 us with 7 (the C=128 / L=16 layers sweep a full M=128 tile whatever it holds), so smaller tiles
@@ -1309,6 +1311,12 @@ static int build_fused(UnetImpl* net, int B, int by_slot, bool keep_all, cudaStr
   P.by_slot = by_slot;
   *out = st;
   return MMDK_OK;
+}
+
+uint64_t unet_fused_state_uid(const UnetImpl* net, int B) {
+  auto it = net->fused.find(B);
+  if (it == net->fused.end() || it->second->keep_all != net->fused_keep) return 0;   // not built, or about to be rebuilt
+  return it->second->uid;
 }
 
 int unet_forward_fused(UnetImpl* net, const float* x, int B, int t, float* eps, cudaStream_t stream) {

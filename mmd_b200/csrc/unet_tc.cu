@@ -446,6 +446,7 @@ struct TcOpHost {
 };
 
 struct TcState {
+  uint64_t uid = 0;
   int n_tiles = 0, B = 0;
   std::vector<TcImage> images;   // [0] = network input image, [1 + j] = output of op j
   std::vector<TcOpHost> ops;
@@ -502,6 +503,7 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
   const auto& cfg = net->cfg;
   if (cfg.self_attention) return fail(MMDK_EINVAL, "tensor-core executor: LinearAttention not supported");
   auto* st = new TcState();
+  st->uid = next_uid();
   st->B = B;
   st->n_tiles = (B + ST - 1) / ST;
   const int n_ops = (int)net->ops.size();
@@ -695,6 +697,11 @@ static int build_tc(UnetImpl* net, int B, cudaStream_t stream) {
   if (check_cuda(cudaGetLastError(), "tensor-core executor setup") != MMDK_OK) { tc_free(st); return MMDK_ECUDA; }
   net->tc = st;
   return MMDK_OK;
+}
+
+uint64_t unet_tc_state_uid(const UnetImpl* net, int B) {
+  auto it = net->tc_cache.find(B);
+  return it == net->tc_cache.end() ? 0 : it->second->uid;
 }
 
 int unet_forward_tc(UnetImpl* net, int mode, const float* x, int B, int t, float* eps, cudaStream_t stream) {

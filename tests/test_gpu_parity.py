@@ -200,6 +200,40 @@ def test_dim_mults_option1_chain(dev):
         assert torch.equal(ch[0], chain)
 
 
+def test_graph_replay_follows_weight_reloads_and_state_eviction(dev):
+    """The batched sampler replays a captured CUDA graph that bakes in device pointers of the UNet handle (weights, cond table)
+    and of the executor state of its batch size (activation images).  Both can be destroyed and re-created: a weight reload
+    rebuilds the handle, and forwards at many other batch sizes evict the bounded per-batch-size state cache.  The graph key
+    carries their unique ids, so a stale graph is never replayed."""
+    import mmd_b200 as M
+    T, K = 25, 8
+    o = build_oracle("EnvEmpty2D", T=T, w_smooth=0.0)
+    p = build_product(dev, "EnvEmpty2D", T=T, P=o["P"], w_smooth=0.0, precision="f16x3")
+    hc = {k: v.to(dev) for k, v in port.hard_conds_from_start_goal(torch.tensor([-0.8, 0.0]), torch.tensor([0.8, 0.1]), o["norm"]).items()}
+    noise = torch.randn(T + 2, K, 64, 4, device=dev, generator=torch.Generator(device=dev).manual_seed(4))   # step-major: stable pointer
+    mk = lambda: M.MultiRobotSampler(p["model"], p["guide"], n_guide_steps=20, t_start_guide=math.ceil(0.5 * T), noise_std=0.5,
+                                     n_diffusion_steps_without_noise=1)
+    smp = mk()
+    run = lambda s: s.sample([hc], K, noise=noise, mode="independent").clone()
+    a1, a2 = run(smp), run(smp)            # capture, replay
+    assert torch.equal(a1, a2)
+    # (1) executor states of other batch sizes push this one out of the bounded cache; it is rebuilt with new buffers
+    for B in (3, 5, 6, 7, 9, 10):
+        p["unet"].forward_t(torch.randn(B, 64, 4, device=dev), 3, precision="f16x3")
+    torch.cuda.synchronize()
+    junk = [torch.full((1 << 20,), float("nan"), device=dev) for _ in range(64)]   # recycle freed blocks with poison
+    a3 = run(smp)
+    assert torch.equal(a3, a1), "replayed a graph over an evicted executor state"
+    del junk
+    # (2) new weights through the parent module: the native handle is rebuilt (often at the same host address)
+    P2 = port.make_unet_params(seed=5)
+    p["model"].load_state_dict({f"model.{k}": v for k, v in P2.items()}, strict=False)
+    b1 = run(smp)
+    fresh = run(mk())
+    assert not torch.equal(b1, a1), "replayed a graph over the old weights"
+    assert torch.equal(b1, fresh)
+
+
 def test_cell_index_bit_exact(pair, dev):
     import ctypes as C
     from mmd_b200 import _lib
