@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._gridpack import packed_grid
 
 
 def _f(v):
@@ -60,9 +61,6 @@ class ConstraintSet:
         self.bucket_ptr = torch.stack(bps, 0) if bps else torch.zeros(0, H + 1, dtype=torch.int32)
         self.cons = torch.cat(entries, 0) if entries else torch.zeros(0, 4, device=device)
         self.weights = torch.tensor([float(w) for w in weights], dtype=torch.float32)
-
-
-_PACKED_GRIDS = {}   # (id(grid object), device) -> (grid object, packed float4 grid on the device)
 
 
 class GuideManagerTrajectoriesWithVelocity(nn.Module):
@@ -118,20 +116,7 @@ class GuideManagerTrajectoriesWithVelocity(nn.Module):
         return list(self.extra_cost_l), list(self.extra_costs_grad_weight_l)
 
     def _pack_grid(self, grid_obj, device):
-        # process-wide: every planner of a fleet builds its own guide over the SAME grid object (envs._GRID_CACHE, or the
-        # reference's own GridMapSDF), and packing + uploading 2.5 MB per planner dominated a planner's first call
-        key = (id(grid_obj), str(device))
-        hit = _PACKED_GRIDS.get(key)
-        if hit is None or hit[0] is not grid_obj:   # the entry keeps grid_obj alive, so a live id can never be recycled
-            sdf = torch.as_tensor(grid_obj.sdf_tensor, dtype=torch.float32)
-            grad = torch.as_tensor(grid_obj.grad_sdf_tensor, dtype=torch.float32)
-            packed = torch.zeros(sdf.shape[0], sdf.shape[1], 4, dtype=torch.float32)
-            packed[..., 0] = sdf.cpu()
-            packed[..., 1:3] = grad.cpu()
-            if len(_PACKED_GRIDS) >= 16:
-                _PACKED_GRIDS.pop(next(iter(_PACKED_GRIDS)))
-            hit = _PACKED_GRIDS[key] = (grid_obj, packed.to(device).contiguous())
-        return hit[1]
+        return packed_grid(grid_obj, device)   # process-wide cache (mmd_b200/_gridpack.py)
 
     def lower_env(self, device):
         """mmdk_guide_env from the CostComposite (mpd.py:215-255)."""

@@ -8,6 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from ._gridpack import packed_grid
 
 ROBOT_PLANAR_DISK_RADIUS = 0.05  # mmd/config/mmd_params.py:30
 
@@ -84,13 +85,7 @@ class PlanningTask:
         keep = None
         grid = self.env.grid_map_sdf_obj_fixed
         if grid is not None:
-            key = str(device)
-            if key not in self._packed:
-                packed = torch.zeros(*grid.sdf_tensor.shape, 4)
-                packed[..., 0] = grid.sdf_tensor
-                packed[..., 1:3] = grid.grad_sdf_tensor
-                self._packed[key] = packed.to(device).contiguous()
-            keep = self._packed[key]
+            keep = packed_grid(grid, device)   # shared with the guides (mmd_b200/_gridpack.py)
             env.grid_dev = keep.data_ptr()
             env.nx, env.ny = keep.shape[0], keep.shape[1]
             md = torch.abs(self.env.limits[1] - self.env.limits[0])
