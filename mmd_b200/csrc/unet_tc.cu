@@ -15,6 +15,11 @@
 // with M = 128 rows per MMA (n_mt MMAs tiles per image), N = cout, K = 16 per instruction.
 // Images move global<->shared with bulk async copies (TMA, UBLKCP) completing on mbarriers; weights stream through a
 // 3-stage ring; one elected thread issues tcgen05.mma; four warps run the epilogue straight out of TMEM.
+//
+// 4-level networks (dim_mults (1,2,4,8), temporal_unet.py:17-20): 256-channel conv blocks run as gridDim.y = 2 output-channel
+// slices of N = 128 (GroupNorm groups are channel-contiguous: a slice owns 4 whole groups, template parameter NG = 4), and ops
+// whose source images do not fit shared memory together (the 512-channel concat at L = 8 and the block that adds its 1x1
+// residual conv) STREAM them: one image per input phase through the same buffer, accumulating in TMEM across phases.
 #include <algorithm>
 #include <map>
 #include <string>
