@@ -1,6 +1,7 @@
 """Host-side logic of mmd_b200 that needs no GPU: schedule buffers, env grids, constraint bucketing, lowering."""
 import math
 
+import pytest
 import torch
 
 import mmd_b200 as M
@@ -197,3 +198,21 @@ def test_cross_cond_entries_match_the_reference_vectors():
         r, b = torch.tensor(list(cc.rel)), torch.tensor(list(cc.bnd))
         a1 = torch.min(x[1][:, 0, :] + r, b)
         assert torch.equal(y[0][:, 63, :], a1) and torch.equal(y[1][:, 0, :], torch.max(a1 - r, -b))
+
+
+@pytest.mark.parametrize("dim_mults", [(1, 2, 4), (1, 2, 4, 8), (1, 2)])
+def test_layer_program_mirrors_the_oracle_forward(dim_mults):
+    """TemporalUnet._layer_program() (the shapes the executor-selection logic reasons about) lists exactly the ops the oracle's
+    forward executes (temporal_unet.py:121-174), in order, with the same output channels and lengths."""
+    P = port.make_unet_params(seed=1, dim_mults=dim_mults)
+    taps = {}
+    port.unet_forward(P, torch.randn(2, 64, 4), torch.zeros(2, dtype=torch.long), taps=taps)
+    u = M.TemporalUnet(n_support_points=64, state_dim=4, unet_input_dim=32, dim_mults=dim_mults)
+    prog = u._layer_program()
+    assert prog[-1][0] == "final" and len(prog) == len(taps["ops"]) + 1
+    for (kind, srcs, res_srcs, cout, L), (name, act) in zip(prog, taps["ops"]):
+        l_out = L // 2 if kind == "down" else (2 * L if kind == "up" else L)
+        assert (act.shape[1], act.shape[2]) == (cout, l_out), (name, kind, cout, L)
+        # a block carries the RTB's 1x1 residual conv exactly where the checkpoint has one
+        if kind == "block" and name.endswith(".blocks.1"):
+            assert bool(res_srcs) == (name[:-len(".blocks.1")] + ".residual_conv.weight" in P), name
