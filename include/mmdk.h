@@ -267,7 +267,10 @@ int mmdk_run_chain(const mmdk_unet* net, int unet_mode, const mmdk_guide_env* en
  * in ONE call: for every step i, for every tile m in order
  *   mmdk_unet_forward(tile m, t_index[i]) -> mmdk_ddpm_step(tile m, scalars[i], noise frame i; the step applies the tile's
  *   hard conditions itself) -> every cross condition (apply_cross_conditioning, sample_functions.py:17-31)
- * and, after the last tile of the step, the chain frame i of every tile (the state AFTER all stitches, :103-105).
+ * and, after the last tile of the step, the chain frame i of every tile (the state AFTER all stitches, :103-105).  The reference
+ * records x[m] itself (no clone) and stitches in place, so the stitch after tile m's step also rewrites the stitched waypoint of the
+ * previously recorded frame of every tile not stepped yet in that reverse step; reproduced (chain_init_dev = the frame before
+ * step 0).
  * A tile's batch is n_groups planner calls of K samples (mmdk_groups), so R multi-tile planner calls run as one chain; a cross
  * condition applies to the batch rows [row_lo, row_hi) (planner calls that share the tile transforms).  use_graph != 0:
  * captured once into a CUDA graph keyed on every pointer / scalar, replayed afterwards. */
@@ -282,6 +285,7 @@ typedef struct {
   float* eps_dev;                     /* [B, H, D] scratch */
   const float* noise_dev;             /* [n_steps, B, H, D] or NULL */
   float* chain_out_dev;               /* [n_steps, B, H, D] or NULL */
+  float* chain_init_dev;              /* [B, H, D] or NULL: the frame recorded BEFORE the first step (it aliases x in the reference, see below) */
 } mmdk_ensemble_tile;
 
 typedef struct {

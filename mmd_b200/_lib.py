@@ -63,7 +63,7 @@ class ChainDesc(C.Structure):
 class EnsembleTile(C.Structure):
     _fields_ = [("net", C.c_void_p), ("unet_mode", C.c_int), ("env", C.POINTER(GuideEnv)), ("groups", C.POINTER(Groups)),
                 ("scalars", C.POINTER(StepScalars)), ("x_dev", C.c_void_p), ("eps_dev", C.c_void_p), ("noise_dev", C.c_void_p),
-                ("chain_out_dev", C.c_void_p)]
+                ("chain_out_dev", C.c_void_p), ("chain_init_dev", C.c_void_p)]
 
 
 class CrossCond(C.Structure):

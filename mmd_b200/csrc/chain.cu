@@ -217,13 +217,30 @@ int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph,
   }
   cudaStream_t s = (cudaStream_t)stream;
   auto issue = [&](cudaStream_t q) -> int {
-    auto cross_all = [&]() -> int {
+    // m_done: the tile that has just been stepped in reverse step `step` (-1: none).  The reference appends x[m] itself to its
+    // chain lists (diffusion_ensemble.py:77,103-105: no clone) and apply_cross_conditioning writes in place, so the stitch that
+    // follows tile m's step also rewrites the stitched waypoint of the frame already recorded for every tile that has NOT been
+    // stepped yet in this reverse step (its x is still the recorded tensor).  Reproduced here: the row goes into that frame too.
+    auto cross_all = [&](int m_done, int step) -> int {
       for (int c = 0; c < ens->n_cross; ++c) {
         const mmdk_cross_cond& cc = ens->cross[c];
         const size_t o = (size_t)cc.row_lo * H * MMDK_STATE_DIM;
         int rc = mmdk_cross_condition(ens->tiles[cc.m1].x_dev + o, ens->tiles[cc.m2].x_dev + o, cc.row_hi - cc.row_lo, H, cc.ind1,
                                       cc.ind2, cc.rel, cc.bnd, q);
         if (rc != MMDK_OK) return rc;
+        for (int side = 0; side < 2; ++side) {
+          const int tm = side ? cc.m2 : cc.m1;
+          int ind = side ? cc.ind2 : cc.ind1;
+          if (tm <= m_done || cc.row_hi <= cc.row_lo) continue;
+          const mmdk_ensemble_tile& t = ens->tiles[tm];
+          const size_t frame = (size_t)t.groups->n_groups * t.groups->K * H * MMDK_STATE_DIM;
+          float* prev = (step == 0) ? t.chain_init_dev : (t.chain_out_dev ? t.chain_out_dev + (size_t)(step - 1) * frame : nullptr);
+          if (!prev) continue;
+          if (ind < 0) ind += H;
+          const size_t off = o + (size_t)ind * MMDK_STATE_DIM, pitch = (size_t)H * MMDK_STATE_DIM * sizeof(float);
+          MMDK_CUDA(cudaMemcpy2DAsync(prev + off, pitch, t.x_dev + off, pitch, MMDK_STATE_DIM * sizeof(float),
+                                      (size_t)(cc.row_hi - cc.row_lo), cudaMemcpyDeviceToDevice, q));
+        }
       }
       return MMDK_OK;
     };
@@ -237,7 +254,7 @@ int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph,
         rc = mmdk_ddpm_step(t.env, t.groups, &t.scalars[i], H, t.x_dev, t.eps_dev, t.noise_dev ? t.noise_dev + (size_t)i * frame : nullptr,
                             nullptr, q);
         if (rc != MMDK_OK) return rc;
-        rc = cross_all();   // diffusion_ensemble.py:99-101: after EVERY tile's step
+        rc = cross_all(m, i);   // diffusion_ensemble.py:99-101: after EVERY tile's step
         if (rc != MMDK_OK) return rc;
       }
       for (int m = 0; m < ens->n_tiles; ++m) {   // the chain frame holds the step's state after all stitches (:103-105)
@@ -272,6 +289,7 @@ int mmdk_run_chain_ensemble(const mmdk_ensemble_desc* ens, int H, int use_graph,
     key.words.push_back((uint64_t)(uintptr_t)t.eps_dev);
     key.words.push_back((uint64_t)(uintptr_t)t.noise_dev);
     key.words.push_back((uint64_t)(uintptr_t)t.chain_out_dev);
+    key.words.push_back((uint64_t)(uintptr_t)t.chain_init_dev);
     push_bytes(key, t.env, sizeof(*t.env));
     push_bytes(key, t.groups, sizeof(*t.groups));
     push_bytes(key, t.scalars, sizeof(mmdk_step_scalars) * ens->n_steps);

@@ -219,7 +219,8 @@ def cross_cond_entries(cross_conds, transforms, D, row_lo, row_hi):
     return out
 
 
-def run_ensemble_chain_native(models, lowered, step_list, x, eps, noise_steps, chain_steps, cross_entries, use_graph=False):
+def run_ensemble_chain_native(models, lowered, step_list, x, eps, noise_steps, chain_steps, cross_entries, use_graph=False,
+                              chain_init=None):
     """One mmdk_run_chain_ensemble call: the multi-tile reverse loop of DiffusionsEnsemble.p_sample_loop
     (diffusion_ensemble.py:78-106).  models / lowered / x / eps / noise_steps / chain_steps: dicts keyed by tile (tiles must be
     0..n-1 in order); step_list[m] = [(t_index, StepScalars)] per tile; noise_steps[m] / chain_steps[m]: contiguous
@@ -251,6 +252,8 @@ def run_ensemble_chain_native(models, lowered, step_list, x, eps, noise_steps, c
         te.x_dev, te.eps_dev = x[m].data_ptr(), eps[m].data_ptr()
         te.noise_dev = noise_steps[m].data_ptr() if noise_steps is not None and noise_steps.get(m) is not None else None
         te.chain_out_dev = chain_steps[m].data_ptr() if chain_steps is not None and chain_steps.get(m) is not None else None
+        # the frame recorded before the first step: in the reference it IS x[m] until tile m is stepped (aliasing, mmdk.h)
+        te.chain_init_dev = chain_init[m].data_ptr() if chain_init is not None and chain_init.get(m) is not None else None
     cross_arr = (_lib.CrossCond * max(1, len(cross_entries)))(*cross_entries)
     desc = _lib.EnsembleDesc()
     desc.n_tiles, desc.tiles, desc.n_steps, desc.t_index = len(tiles), tile_arr, n, t_arr

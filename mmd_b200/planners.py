@@ -422,7 +422,8 @@ class DiffusionsEnsemble(nn.Module):
             for m in tiles:
                 chain[m][0].copy_(x[m])
         run_ensemble_chain_native(self.models, lowered, step_list, x, eps, nz, {m: chain[m][1:] for m in tiles} if return_chain else None,
-                                  cross_cond_entries(cross_conds, self.transforms, D, 0, B))
+                                  cross_cond_entries(cross_conds, self.transforms, D, 0, B),
+                                  chain_init={m: chain[m][0] for m in tiles} if return_chain else None)
         if return_chain:
             return x, {m: chain[m].transpose(0, 1) for m in tiles}   # [B, steps + 1, H, D] like torch.stack(chain, dim=1)
         return x
@@ -841,7 +842,7 @@ def _plan_batch_ensemble(planners: List["MPDEnsemble"], constraints_l_l, rng="se
         ev[0].record()
         # the whole multi-tile chain of all planner calls: one native call (mmdk_run_chain_ensemble)
         run_ensemble_chain_native(p0.models, lowered, step_list, x, eps, {m: noise[m][1:] for m in tiles},
-                                  {m: chains[m][1:] for m in tiles}, cross_entries)
+                                  {m: chains[m][1:] for m in tiles}, cross_entries, chain_init={m: chains[m][0] for m in tiles})
         ev[1].record()
         torch.cuda.synchronize()
         t_total = time.perf_counter() - t0

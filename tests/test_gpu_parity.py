@@ -680,8 +680,8 @@ def test_plan_batch_equals_sequential_calls(dev):
 
 def test_diffusions_ensemble_two_tiles(dev):
     """DiffusionsEnsemble.run_inference (diffusion_ensemble.py:56-106,224-268): two tiles stitched by cross conditioning
-    (63 -> 0 through the (2, 0) tile transform).  Final frames vs the oracle (chain frames of later tiles alias in the
-    reference, oracle/port.py ensemble_p_sample_loop)."""
+    (63 -> 0 through the (2, 0) tile transform).  Final frames and the recorded chain vs the oracle (chain frames of later
+    tiles alias in the reference, oracle/port.py ensemble_p_sample_loop: reproduced by mmdk_run_chain_ensemble)."""
     import mmd_b200 as M
     T, K = 25, 6
     o = build_oracle("EnvEmptyNoWait2D", T=T, w_smooth=0.0)
@@ -703,13 +703,23 @@ def test_diffusions_ensemble_two_tiles(dev):
     ens = M.DiffusionsEnsemble({0: p0["model"], 1: p1["model"]}, {m: t.to(dev) for m, t in transforms.items()})
     skw = [dict(guide=p0["guide"], n_guide_steps=20, t_start_guide=13, noise_std_extra_schedule_fn=lambda x: 0.5),
            dict(guide=p1["guide"], n_guide_steps=20, t_start_guide=13, noise_std_extra_schedule_fn=lambda x: 0.5)]
-    out = ens.run_inference(None, {m: {k: v.to(dev) for k, v in h.items()} for m, h in hard.items()}, cross,
-                            n_samples=K, return_chain=False, sample_kwargs=skw, n_diffusion_steps_without_noise=1,
-                            noise={m: n.to(dev) for m, n in noise.items()})
+    chains = ens.run_inference(None, {m: {k: v.to(dev) for k, v in h.items()} for m, h in hard.items()}, cross,
+                               n_samples=K, return_chain=True, sample_kwargs=skw, n_diffusion_steps_without_noise=1,
+                               noise={m: n.to(dev) for m, n in noise.items()})
     for m in (0, 1):
-        e = _per_traj(out[m], ref[m][-1])
+        assert chains[m].shape == ref[m].shape == (T + 2, K, 64, 4)
+        e = _per_traj(chains[m][-1], ref[m][-1])
         print(f"ensemble tile {m}: median={float(e.median()):.2e} max={float(e.max()):.2e}")
         assert float(e.median()) < 1e-4 and float(e.max()) < 2e-2
+    # every recorded frame, including the reference's aliasing: frame k of tile 1 carries the stitched first waypoint of
+    # reverse step k + 1 (the reference records x[1] itself and stitches in place after tile 0's step)
+    stitch = (chains[1][:-1, :, 0, :].cpu() - ref[1][:-1, :, 0, :]).abs().max()
+    print(f"ensemble chain frames: stitched waypoint of the recorded frames vs oracle max abs {float(stitch):.2e}")
+    assert float(stitch) < 2e-3
+    for k in range(0, T + 2, 5):
+        for m in (0, 1):
+            e = _per_traj(chains[m][k], ref[m][k])
+            assert float(e.median()) < 1e-4 and float(e.max()) < 2e-2, (k, m)
 
 
 def test_mpd_ensemble_planner(dev):
