@@ -209,3 +209,45 @@ def test_soft_constraints_from_other_agents_matches_reference(ref):
         assert torch.equal(torch.stack(out[0].get_q_l()), q)
         assert torch.equal(torch.tensor(out[0].get_t_range_l(), dtype=torch.float32), rng)
         assert torch.allclose(torch.tensor(out[0].radius_l), rad) and out[0].is_soft
+
+
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_ensemble_loop_bit_exact(direction):
+    """port.ensemble_p_sample_loop == the reference's DiffusionsEnsemble.p_sample_loop (diffusion_ensemble.py:56-106) on scripted
+    noise, for a robot crossing the 1x2 tile grid in either direction (tile transforms (0,0),(2,0) or (2,0),(0,0)): every
+    recorded chain frame, i.e. including the reference's aliasing of the recorded frames with the in-place stitch."""
+    from math import ceil
+    from oracle import ref_build
+    ref_shim.install()
+    from mmd.models.diffusion_models.diffusion_ensemble import DiffusionsEnsemble
+    from mmd.models.diffusion_models.sample_functions import ddpm_sample_fn
+    T, K = 25, 3
+    P = port.make_unet_params(seed=0)
+    tiles = {m: ref_build.build_reference("EnvEmptyNoWait2D", T, P, cutoff_margin=0.01) for m in (0, 1)}
+    tr = {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}
+    if direction == "backward":
+        tr = {0: tr[1], 1: tr[0]}
+    norm = port.LimitsNormalizer(*port.DEFAULT_NORMALIZER_LIMITS)
+    s0 = norm.normalize(torch.tensor([-0.7, 0.1, 0.0, 0.0]))
+    g1 = norm.normalize(torch.tensor([0.6, -0.2, 0.0, 0.0]))
+    hard = {0: {0: s0}, 1: {63: g1}}
+    cross = {(0, 1): (63, 0)}
+    g = torch.Generator().manual_seed(5)
+    noise = {m: torch.randn(T + 2, K, 64, 4, generator=g) for m in (0, 1)}
+    # the reference's draw order: x_T per tile, then per step, per tile (diffusion_ensemble.py:68-95)
+    script = [noise[0][0], noise[1][0]] + [noise[m][k] for k in range(1, T + 2) for m in (0, 1)]
+    ens = DiffusionsEnsemble({m: tiles[m]["model"] for m in (0, 1)}, tr)
+    skw = [dict(guide=tiles[m]["guide"], n_guide_steps=20, t_start_guide=ceil(0.5 * T), noise_std_extra_schedule_fn=lambda x: 0.5)
+           for m in (0, 1)]
+    hc_ref = {m: {k: v.reshape(1, -1).repeat(K, 1) for k, v in h.items()} for m, h in hard.items()}
+    with ref_build.scripted_noise(script), ref_build.quiet():
+        _, chains = ens.p_sample_loop((K, 64, 4), hc_ref, dict(cross), n_diffusion_steps=T, return_chain=True, sample_fn=ddpm_sample_fn,
+                                      n_diffusion_steps_without_noise=1, sample_kwargs=skw)
+    sdf, grad = port.build_sdf_grid("EnvEmptyNoWait2D")
+    guides = {m: port.GuideSpec(port.GridSDF(sdf, grad), norm, cutoff_margin=0.01) for m in (0, 1)}
+    kw = {m: dict(guide=guides[m], n_guide_steps=20, t_start_guide=ceil(0.5 * T), noise_std=0.5) for m in (0, 1)}
+    model = port.DiffusionModel(P, T)
+    mine = port.ensemble_p_sample_loop({0: model, 1: model}, {m: port.repeat_hard_conds(h, K) for m, h in hard.items()}, dict(cross),
+                                       tr, noise, T, 1, kw)
+    for m in (0, 1):
+        assert torch.equal(chains[m].transpose(0, 1), mine[m]), (direction, m)
