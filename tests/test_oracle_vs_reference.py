@@ -251,3 +251,44 @@ def test_ensemble_loop_bit_exact(direction):
                                        tr, noise, T, 1, kw)
     for m in (0, 1):
         assert torch.equal(chains[m].transpose(0, 1), mine[m]), (direction, m)
+
+
+def test_split_cost_constraints_to_tasks_matches_reference():
+    """MPDEnsemble.split_cost_constraints_to_tasks (mpd_ensemble.py:431-507): same tiles, same object order (hard objects, then
+    soft), same entries as the reference method run on the reference's own CostConstraint objects -- and the installed
+    constraints (waypoint ranges - task_id * 64, positions - tile transform, :516-517) agree too."""
+    import contextlib
+    import io
+    import types
+    import mmd_b200 as M
+    from oracle import ref_build
+    ref_shim.install()
+    from mmd.planners.single_agent.mpd_ensemble import MPDEnsemble as RefEns
+    r = ref_build.build_reference("EnvEmptyNoWait2D", 25, None, with_model=False)
+    task_stub = types.SimpleNamespace(infer_task_id_from_q_idx=lambda q_idx: (int(q_idx // 64), None))
+    ref_self = types.SimpleNamespace(task=task_stub, robot=r["robot"], n_support_points=64, tensor_args=r["tensor_args"])
+    ta = {"device": torch.device("cpu"), "dtype": torch.float32}
+    our_self = types.SimpleNamespace(task=task_stub, robot=M.RobotPlanarDisk(tensor_args=ta), n_support_points=64, tensor_args=ta)
+    g = torch.Generator().manual_seed(3)
+    specs = []   # (qs, ranges, radii, is_soft): entries in both tiles, hard and soft, interleaved
+    for is_soft, n in ((True, 7), (False, 4), (True, 3)):
+        qs = torch.rand(n, 2, generator=g) * 4 - 1
+        h0 = torch.randint(0, 127, (n,), generator=g)
+        specs.append((qs, torch.stack((h0, h0 + 2), -1).float(), torch.rand(n, generator=g) * 0.2 + 0.05, is_soft))
+    ref_cc = [ref_build.make_cost_constraint(r, qs, rng, rad, is_soft=s) for qs, rng, rad, s in specs]
+    our_cc = [M.CostConstraint(our_self.robot, 64, q_l=list(qs), traj_range_l=[tuple(int(v) for v in t) for t in rng.tolist()],
+                               radius_l=rad.tolist(), is_soft=s, tensor_args=ta) for qs, rng, rad, s in specs]
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = RefEns.split_cost_constraints_to_tasks(ref_self, ref_cc)
+    b = M.MPDEnsemble.split_cost_constraints_to_tasks(our_self, our_cc)
+    assert list(a.keys()) == list(b.keys())
+    transforms = {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}
+    for task_id in a:
+        assert [c.is_soft for c in a[task_id]] == [c.is_soft for c in b[task_id]]
+        for ca, cb in zip(a[task_id], b[task_id]):
+            assert torch.equal(ca.qs, cb.qs) and torch.equal(ca.traj_ranges.float(), cb.traj_ranges.float())
+            assert torch.allclose(torch.as_tensor(ca.radii, dtype=torch.float32), torch.as_tensor(cb.radii, dtype=torch.float32), atol=0, rtol=0)
+            # installation (mpd_ensemble.py:516-517)
+            ra, qa = ca.traj_ranges - task_id * 64, ca.qs - transforms[task_id]
+            rb, qb = cb.traj_ranges - task_id * 64, cb.qs - transforms[task_id]
+            assert torch.equal(ra.float(), rb.float()) and torch.equal(qa, qb)
