@@ -292,3 +292,54 @@ def test_split_cost_constraints_to_tasks_matches_reference():
             ra, qa = ca.traj_ranges - task_id * 64, ca.qs - transforms[task_id]
             rb, qb = cb.traj_ranges - task_id * 64, cb.qs - transforms[task_id]
             assert torch.equal(ra.float(), rb.float()) and torch.equal(qa, qb)
+
+
+def test_combine_trajs_matches_reference():
+    """PlanningTaskEnsemble.combine_trajs (tasks_ensemble.py:162-238): tile chains moved into the global frame and concatenated,
+    a sample is free iff it is free in every tile, costs / best trajectory recomputed on the combined free set -- compared field
+    by field with the reference method on CPU (the reference's `trajs_final_coll` indexes the wrong dimension, :186: not compared)."""
+    import types
+    import mmd_b200 as M
+    from oracle import ref_build
+    ref_shim.install()
+    from torch_robotics.tasks.tasks_ensemble import PlanningTaskEnsemble as RefPTE
+    r = {m: ref_build.build_reference("EnvEmptyNoWait2D", 25, None, with_model=False, cutoff_margin=0.01) for m in (0, 1)}
+    tr = {0: torch.tensor([0.0, 0.0]), 1: torch.tensor([2.0, 0.0])}
+    ta = {"device": torch.device("cpu"), "dtype": torch.float32}
+    ref_self = types.SimpleNamespace(transforms=tr, robot=r[0]["robot"], tensor_args=ta)
+    ref_self.transform_q = lambda task_id, q: RefPTE.transform_q(ref_self, task_id, q)
+    ours = M.PlanningTaskEnsemble.__new__(M.PlanningTaskEnsemble)
+    ours.transforms, ours.horizon, ours.tensor_args = tr, 64, ta
+    ours.robot = M.RobotPlanarDisk(tensor_args=ta)
+    ours.robot.dt = r[0]["robot"].dt
+    g = torch.Generator().manual_seed(11)
+    K, S = 6, 5
+    t = torch.linspace(0, 1, 64)[None, :, None]
+    def chain():
+        a, b = torch.rand(K, 1, 2, generator=g) * 1.6 - 0.8, torch.rand(K, 1, 2, generator=g) * 1.6 - 0.8
+        pos = a * (1 - t) + b * t + 0.02 * torch.randn(K, 64, 2, generator=g)
+        x = torch.cat((pos, torch.randn(K, 64, 2, generator=g) * 0.1), -1)
+        return torch.stack([x + 0.01 * s for s in range(S)])
+    for coll in ({0: [1, 4], 1: [4]}, {0: [], 1: []}, {0: [0, 1, 2, 3, 4, 5], 1: []}):
+        res_ref, res_our = {}, {}
+        for m in (0, 1):
+            it = chain()
+            ci = torch.tensor(coll[m], dtype=torch.long)
+            fi = torch.tensor([i for i in range(K) if i not in coll[m]], dtype=torch.long)
+            base = dict(trajs_iters=it, trajs_final=it[-1], trajs_final_coll=it[-1][ci] if len(ci) else None,
+                        trajs_final_free=it[-1][fi] if len(fi) else None, t_total=0.5)
+            res_ref[m] = dict(base, trajs_final_coll_idxs=ci, trajs_final_free_idxs=fi)
+            res_our[m] = dict({k: (v.clone() if torch.is_tensor(v) else v) for k, v in base.items()},
+                              trajs_final_coll_idxs=ci[:, None].clone(), trajs_final_free_idxs=fi[:, None].clone())
+        a = RefPTE.combine_trajs(ref_self, res_ref)
+        b = ours.combine_trajs(res_our)
+        assert torch.equal(a["trajs_iters"], b["trajs_iters"])
+        assert a["trajs_final_coll_idxs"].tolist() == b["trajs_final_coll_idxs"].tolist()
+        assert a["trajs_final_free_idxs"].tolist() == b["trajs_final_free_idxs"].tolist()
+        assert (a["success_free_trajs"], a["fraction_free_trajs"]) == (b["success_free_trajs"], b["fraction_free_trajs"])
+        if a["success_free_trajs"]:
+            assert torch.equal(a["trajs_final_free"], b["trajs_final_free"])
+            for k in ("cost_smoothness_trajs_final_free", "cost_path_length_trajs_final_free", "cost_all_trajs_final_free",
+                      "variance_waypoint_trajs_final_free", "cost_best_free_traj", "traj_final_free_best"):
+                assert torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), k
+            assert int(a["idx_best_traj"]) == int(b["idx_best_traj"])
